@@ -1,0 +1,11 @@
+"""dawnsearch_b200 -- B200-native exact top-k search behind DawnSearch's index add/search interface.
+
+Only the hot path lives here: `csrc/` (hand-written sm_100a kernels + the C ABI in
+include/dawn_index.h) and `index.py`, a ctypes mirror of the `usearch::ffi::Index` surface the
+reference calls (src/search/search_provider.rs).  There is no CPU fallback.
+"""
+from .index import (EM_LEN, MAX_K, DawnError, Index, IndexOptions, Matches, MetricKind, ScalarKind,
+                    load_library, merge_results_device, new_index)
+
+__all__ = ["EM_LEN", "MAX_K", "DawnError", "Index", "IndexOptions", "Matches", "MetricKind",
+           "ScalarKind", "load_library", "merge_results_device", "new_index"]

@@ -1,0 +1,125 @@
+// dawn_common.cuh -- shared device/host definitions for libdawn_b200.so (sm_100a only).
+//
+// Domain vocabulary follows the reference (dawn-search/dawnsearch v0.2.0):
+//   page vector / embedding : 384 x f32 unit vector     (src/search/vector.rs:26-28)
+//   label                   : caller-supplied u64 page id (SQLite rowid,
+//                             src/search/search_provider.rs:145,275)
+//   distance                : 1 - dot, smaller is better  (src/search/vector.rs:128-134)
+// "row" is the position of a page vector inside this GPU's corpus shard.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dawn {
+
+constexpr int kDim = 384;                       // EM_LEN, src/search/vector.rs:26
+constexpr int kRowBytesF16 = kDim * 2;          // 768 B per stored fp16 page vector
+constexpr int kMaxCand = 128;                   // largest candidate-list length (k + slack)
+constexpr uint32_t kNoRow = 0xFFFFFFFFu;
+constexpr uint64_t kNoLabel = 0xFFFFFFFFFFFFFFFFull;
+
+// One top-k candidate.  16 bytes so it moves as a single 128-bit access.
+struct __align__(16) Cand {
+    float score;     // dot product (approximate order of summation until re-scored)
+    uint32_t row;    // row inside the shard, kNoRow for an empty slot
+    uint64_t label;  // page id
+};
+
+__host__ __device__ inline Cand empty_cand() {
+    Cand c;
+#ifdef __CUDA_ARCH__
+    c.score = __int_as_float(0xff800000);  // -inf
+#else
+    c.score = -__builtin_inff();
+#endif
+    c.row = kNoRow;
+    c.label = kNoLabel;
+    return c;
+}
+
+// Total order of the top-k: score descending, then label ascending (north_star:
+// "deterministic tie-break on lower page id"), then row ascending so that the order is
+// strict even if a caller adds the same label twice.  The reference's BestResults
+// (src/search/best_results.rs:44-65) keeps whichever tied entry arrived first; ours is
+// independent of arrival order.
+__host__ __device__ inline bool cand_better(const Cand &a, const Cand &b) {
+    if (a.score != b.score) return a.score > b.score;
+    if (a.label != b.label) return a.label < b.label;
+    return a.row < b.row;
+}
+
+// Monotone map float -> uint so that atomicMax on the uint orders like the float.
+__device__ inline uint32_t float_to_ordered(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ inline float ordered_to_float(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// ---- synthetic corpus (test / bench aid).  Must stay bit-identical to
+// oracle/dawn_oracle.c:dawn_oracle_synth_row_f32 -- integer hash, exact integer sum of
+// squares, then correctly rounded IEEE f64 sqrt / divide / multiply only.
+__host__ __device__ inline uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ inline int32_t synth_raw(uint64_t seed, uint64_t row, uint32_t col) {
+    uint64_t h = mix64(seed + 0x9E3779B97F4A7C15ull * (row * (uint64_t)kDim + col + 1));
+    uint32_t s = (uint32_t)(h & 0xFFFF) + (uint32_t)((h >> 16) & 0xFFFF) +
+                 (uint32_t)((h >> 32) & 0xFFFF) + (uint32_t)(h >> 48);
+    return (int32_t)s - 131070;
+}
+
+// ---- kernel launchers (defined in the .cu files) -------------------------------------
+
+// K1: f32 page vectors -> stored fp16 rows (round to nearest even), appended at dst.
+// Replaces the per-vector work of usearch Index::add (src/search/search_provider.rs:149,284).
+cudaError_t launch_ingest_f16(const float *src_f32, __half *dst, size_t n_rows, cudaStream_t s);
+// Synthetic rows [first_row, first_row+n) written straight into the corpus arena.
+cudaError_t launch_synth_f16(__half *dst, uint64_t seed, uint64_t first_row, size_t n_rows,
+                             cudaStream_t s);
+// Gather stored rows back to f32 (dawn_index_get; SearchProvider::embedding_for_page,
+// src/search/search_provider.rs:183-195, served from the device corpus).
+cudaError_t launch_gather_f32(const __half *corpus, const uint32_t *rows, size_t n, float *out,
+                              cudaStream_t s);
+
+struct ScanLaunch {
+    const __half *corpus;     // [n_rows][384] fp16
+    const uint64_t *labels;   // [n_rows]
+    uint32_t n_rows;
+    const float *queries;     // [nq][384] f32, device
+    int nq;                   // queries in this pass (1, 2 or 4)
+    int kprime;               // candidate list length: 16, 32, 64 or 128
+    Cand *partials;           // [nq][grid][kprime] out
+    uint32_t *chunk_counter;  // zeroed before launch
+    uint32_t *status;         // device word, bit0 = internal buffer overflow (a bug if ever set)
+    int grid;                 // number of CTAs (= SM count)
+};
+// K2: streaming scan + fused per-CTA top-k' (replaces usearch Index::search,
+// src/search/search_provider.rs:214).
+cudaError_t launch_scan_topk_f16(const ScanLaunch &p, cudaStream_t s);
+int scan_max_queries_per_pass(int kprime);
+
+struct FinalizeLaunch {
+    const __half *corpus;
+    const float *queries;   // [nq][384]
+    int nq;
+    const Cand *partials;   // [nq][n_lists][kprime], each list sorted by cand_better
+    int n_lists;
+    int kprime;
+    int k;                  // results wanted per query (<= kprime)
+    float eps;              // bound on |scan score - exact score| used by the certificate
+    uint64_t *labels_out;   // [nq][k]
+    float *distances_out;   // [nq][k]
+    uint32_t *counts_out;   // [nq]
+    uint32_t *flags_out;    // [nq] bit0 = exactness certified
+};
+// K5+K6: merge per-CTA lists, re-score candidates in the reference's order of summation
+// (src/search/vector.rs:128-134), final order and 1 - score.
+cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s);
+
+}  // namespace dawn

@@ -1,0 +1,818 @@
+// dawn_index.cu -- the C ABI (include/dawn_index.h) and the host-side index object:
+// corpus arena in HBM, label table, pinned staging for adds, search workspace, streams.
+//
+// This object takes the place of usearch's `Index` behind the reference's SearchProvider
+// (/root/reference/src/search/search_provider.rs:67,102).  No CPU fallback exists: every
+// compute path launches the kernels in scan_topk.cu / finalize.cu / ingest.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/dawn_index.h"
+#include "dawn_common.cuh"
+
+using namespace dawn;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+constexpr size_t kStageRowsHost = 8192;  // pinned staging: 8192 vectors = 12 MB of f32
+constexpr float kScanEps = 3.0e-5f;      // bound on |scan score - exact score|
+
+// merge kernel for sharded searches, defined at the bottom of this file
+cudaError_t launch_merge_results(const uint64_t *labels, const float *dist, const uint32_t *counts,
+                                 int n_lists, int batch, int k, uint64_t *labels_out, float *dist_out,
+                                 uint32_t *counts_out, cudaStream_t s);
+cudaError_t launch_find_label(const uint64_t *labels, size_t n, uint64_t label, uint32_t *row_out,
+                              cudaStream_t s);
+
+struct EventPair {
+    cudaEvent_t a, b;
+    int kind;  // 0 scan, 1 finalize
+};
+
+}  // namespace
+
+struct dawn_index {
+    std::mutex mu;
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool dead = false;  // sticky CUDA failure
+
+    __half *corpus = nullptr;
+    uint64_t *labels = nullptr;
+    size_t size = 0;      // rows committed to the device
+    size_t capacity = 0;  // logical capacity promised to the caller
+    size_t phys = 0;      // rows actually allocated
+
+    // staged adds (host, pinned) not yet on the device
+    float *h_stage = nullptr;
+    uint64_t *h_stage_labels = nullptr;
+    size_t staged = 0;
+    float *d_stage = nullptr;
+
+    // search workspace
+    size_t q_cap = 0;  // queries
+    float *d_queries = nullptr, *h_queries = nullptr;
+    uint64_t *d_labels_out = nullptr, *h_labels_out = nullptr;
+    float *d_dist_out = nullptr, *h_dist_out = nullptr;
+    uint32_t *d_counts = nullptr, *h_counts = nullptr;
+    uint32_t *d_flags = nullptr, *h_flags = nullptr;
+    size_t out_cap = 0;  // entries of labels/dist out
+    Cand *d_partials = nullptr;
+    size_t partials_cap = 0;
+    uint32_t *d_counters = nullptr;  // one chunk counter per scan pass, + status word at [0]
+    size_t counters_cap = 0;
+    uint32_t *h_word = nullptr;  // pinned scratch word
+
+    bool profiling = false;
+    std::vector<EventPair> pending;
+    std::vector<EventPair> free_events;
+    dawn_profile prof{};
+};
+
+namespace {
+
+#define CK(idx, expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (idx)->dead = true;                                                               \
+            return fail(DAWN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                  \
+        }                                                                                     \
+    } while (0)
+
+int check_alive(dawn_index *idx) {
+    if (!idx) return fail(DAWN_ERR_INVALID, "null index handle");
+    if (idx->dead) return fail(DAWN_ERR_CUDA, "index is in a failed state after an earlier CUDA error");
+    cudaError_t e = cudaSetDevice(idx->device);
+    if (e != cudaSuccess) {
+        idx->dead = true;
+        return fail(DAWN_ERR_CUDA, "cudaSetDevice(%d): %s", idx->device, cudaGetErrorString(e));
+    }
+    return DAWN_OK;
+}
+
+void drain_events(dawn_index *idx) {
+    if (idx->pending.empty()) return;
+    cudaStreamSynchronize(idx->stream);
+    for (auto &p : idx->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            if (p.kind == 0) idx->prof.scan_ms += ms;
+            else idx->prof.finalize_ms += ms;
+        }
+        idx->free_events.push_back(p);
+    }
+    idx->pending.clear();
+}
+
+bool begin_event(dawn_index *idx, int kind, cudaStream_t s, EventPair *out) {
+    if (!idx->profiling) return false;
+    EventPair p;
+    if (!idx->free_events.empty()) {
+        p = idx->free_events.back();
+        idx->free_events.pop_back();
+    } else {
+        if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return false;
+    }
+    p.kind = kind;
+    cudaEventRecord(p.a, s);
+    *out = p;
+    return true;
+}
+
+void end_event(dawn_index *idx, EventPair &p, cudaStream_t s) {
+    cudaEventRecord(p.b, s);
+    idx->pending.push_back(p);
+}
+
+int grow_physical(dawn_index *idx, size_t rows) {
+    if (rows <= idx->phys) return DAWN_OK;
+    if (rows > 0xFFFFFFF0ull) return fail(DAWN_ERR_INVALID, "capacity %zu exceeds 2^32 rows per GPU", rows);
+    size_t want = rows;
+    if (idx->phys > 0) {  // amortise the reference's reserve(size + 1024) pattern
+        size_t geo = idx->phys + idx->phys / 2;
+        if (geo > want) want = geo;
+    }
+    __half *nc = nullptr;
+    uint64_t *nl = nullptr;
+    cudaError_t e = cudaMalloc(&nc, want * kRowBytesF16);
+    if (e != cudaSuccess && want > rows) {
+        cudaGetLastError();
+        want = rows;
+        e = cudaMalloc(&nc, want * kRowBytesF16);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(DAWN_ERR_CAPACITY, "cannot allocate %zu bytes of HBM for %zu vectors: %s",
+                    want * (size_t)kRowBytesF16, want, cudaGetErrorString(e));
+    }
+    e = cudaMalloc(&nl, want * sizeof(uint64_t));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(nc);
+        return fail(DAWN_ERR_CAPACITY, "cannot allocate label table for %zu vectors", want);
+    }
+    if (idx->size > 0) {
+        CK(idx, cudaMemcpyAsync(nc, idx->corpus, idx->size * kRowBytesF16, cudaMemcpyDeviceToDevice, idx->stream));
+        CK(idx, cudaMemcpyAsync(nl, idx->labels, idx->size * sizeof(uint64_t), cudaMemcpyDeviceToDevice, idx->stream));
+        CK(idx, cudaStreamSynchronize(idx->stream));
+    }
+    if (idx->corpus) cudaFree(idx->corpus);
+    if (idx->labels) cudaFree(idx->labels);
+    idx->corpus = nc;
+    idx->labels = nl;
+    idx->phys = want;
+    return DAWN_OK;
+}
+
+// Move staged host vectors to the device corpus: H2D of the f32 rows, K1 convert, labels.
+int flush_staged(dawn_index *idx) {
+    if (idx->staged == 0) return DAWN_OK;
+    const size_t n = idx->staged;
+    CK(idx, cudaMemcpyAsync(idx->d_stage, idx->h_stage, n * kDim * sizeof(float), cudaMemcpyHostToDevice, idx->stream));
+    CK(idx, launch_ingest_f16(idx->d_stage, idx->corpus + idx->size * kDim, n, idx->stream));
+    idx->prof.kernel_launches++;
+    CK(idx, cudaMemcpyAsync(idx->labels + idx->size, idx->h_stage_labels, n * sizeof(uint64_t), cudaMemcpyHostToDevice, idx->stream));
+    CK(idx, cudaStreamSynchronize(idx->stream));
+    idx->size += n;
+    idx->staged = 0;
+    return DAWN_OK;
+}
+
+int choose_kprime(size_t k) {
+    size_t want = k + (k / 8 > 4 ? k / 8 : 4);
+    int kp = 16;
+    while ((size_t)kp < want) kp <<= 1;
+    return kp > kMaxCand ? kMaxCand : kp;
+}
+
+int ensure_query_ws(dawn_index *idx, size_t batch, size_t k) {
+    if (batch > idx->q_cap) {
+        size_t cap = batch < 64 ? 64 : batch;
+        if (idx->d_queries) cudaFree(idx->d_queries);
+        if (idx->h_queries) cudaFreeHost(idx->h_queries);
+        if (idx->d_counts) cudaFree(idx->d_counts);
+        if (idx->h_counts) cudaFreeHost(idx->h_counts);
+        if (idx->d_flags) cudaFree(idx->d_flags);
+        if (idx->h_flags) cudaFreeHost(idx->h_flags);
+        idx->q_cap = 0;
+        CK(idx, cudaMalloc(&idx->d_queries, cap * kDim * sizeof(float)));
+        CK(idx, cudaMallocHost(&idx->h_queries, cap * kDim * sizeof(float)));
+        CK(idx, cudaMalloc(&idx->d_counts, cap * sizeof(uint32_t)));
+        CK(idx, cudaMallocHost(&idx->h_counts, cap * sizeof(uint32_t)));
+        CK(idx, cudaMalloc(&idx->d_flags, cap * sizeof(uint32_t)));
+        CK(idx, cudaMallocHost(&idx->h_flags, cap * sizeof(uint32_t)));
+        idx->q_cap = cap;
+    }
+    if (batch * k > idx->out_cap) {
+        size_t cap = batch * k < 4096 ? 4096 : batch * k;
+        if (idx->d_labels_out) cudaFree(idx->d_labels_out);
+        if (idx->h_labels_out) cudaFreeHost(idx->h_labels_out);
+        if (idx->d_dist_out) cudaFree(idx->d_dist_out);
+        if (idx->h_dist_out) cudaFreeHost(idx->h_dist_out);
+        idx->out_cap = 0;
+        CK(idx, cudaMalloc(&idx->d_labels_out, cap * sizeof(uint64_t)));
+        CK(idx, cudaMallocHost(&idx->h_labels_out, cap * sizeof(uint64_t)));
+        CK(idx, cudaMalloc(&idx->d_dist_out, cap * sizeof(float)));
+        CK(idx, cudaMallocHost(&idx->h_dist_out, cap * sizeof(float)));
+        idx->out_cap = cap;
+    }
+    return DAWN_OK;
+}
+
+// Enqueue the whole search for `batch` device-resident queries on stream `s`.
+int search_enqueue(dawn_index *idx, const float *d_queries, size_t batch, size_t k, int kprime,
+                   uint64_t *d_labels_out, float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags,
+                   cudaStream_t s) {
+    const int grid = idx->sm_count;
+    const size_t need_partials = batch * (size_t)grid * kprime;
+    if (need_partials > idx->partials_cap) {
+        if (idx->d_partials) cudaFree(idx->d_partials);
+        idx->partials_cap = 0;
+        CK(idx, cudaMalloc(&idx->d_partials, need_partials * sizeof(Cand)));
+        idx->partials_cap = need_partials;
+    }
+    const size_t need_counters = batch + 1;
+    if (need_counters > idx->counters_cap) {
+        size_t cap = need_counters < 1024 ? 1024 : need_counters;
+        if (idx->d_counters) cudaFree(idx->d_counters);
+        idx->counters_cap = 0;
+        CK(idx, cudaMalloc(&idx->d_counters, cap * sizeof(uint32_t)));
+        idx->counters_cap = cap;
+    }
+    CK(idx, cudaMemsetAsync(idx->d_counters, 0, need_counters * sizeof(uint32_t), s));
+
+    size_t done = 0;
+    size_t pass = 0;
+    const int max_qt = scan_max_queries_per_pass(kprime);
+    while (done < batch) {
+        size_t left = batch - done;
+        int qt = left >= 4 && max_qt >= 4 ? 4 : (left >= 2 && max_qt >= 2 ? 2 : 1);
+        ScanLaunch sl;
+        sl.corpus = idx->corpus;
+        sl.labels = idx->labels;
+        sl.n_rows = (uint32_t)idx->size;
+        sl.queries = d_queries + done * kDim;
+        sl.nq = qt;
+        sl.kprime = kprime;
+        sl.partials = idx->d_partials + done * (size_t)grid * kprime;
+        sl.chunk_counter = idx->d_counters + 1 + pass;
+        sl.status = idx->d_counters;
+        sl.grid = grid;
+        EventPair ev;
+        bool timed = begin_event(idx, 0, s, &ev);
+        CK(idx, launch_scan_topk_f16(sl, s));
+        if (timed) end_event(idx, ev, s);
+        idx->prof.scan_launches++;
+        idx->prof.kernel_launches++;
+        done += qt;
+        pass++;
+    }
+    FinalizeLaunch fl;
+    fl.corpus = idx->corpus;
+    fl.queries = d_queries;
+    fl.nq = (int)batch;
+    fl.partials = idx->d_partials;
+    fl.n_lists = grid;
+    fl.kprime = kprime;
+    fl.k = (int)k;
+    fl.eps = kScanEps;
+    fl.labels_out = d_labels_out;
+    fl.distances_out = d_dist_out;
+    fl.counts_out = d_counts;
+    fl.flags_out = d_flags;
+    EventPair ev;
+    bool timed = begin_event(idx, 1, s, &ev);
+    CK(idx, launch_finalize(fl, s));
+    if (timed) end_event(idx, ev, s);
+    idx->prof.finalize_launches++;
+    idx->prof.kernel_launches++;
+    idx->prof.queries += batch;
+    if (idx->pending.size() > 4096) drain_events(idx);
+    return DAWN_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+const char *dawn_last_error(void) { return g_last_error.c_str(); }
+const char *dawn_version(void) { return "libdawn_b200 0.1.0 sm_100a"; }
+
+int dawn_index_create(const dawn_options *opts, dawn_index **out) {
+    if (!out) return fail(DAWN_ERR_INVALID, "out is null");
+    *out = nullptr;
+    dawn_options o{};
+    if (opts) o = *opts;
+    if (o.dimensions != 0 && o.dimensions != DAWN_DIMENSIONS)
+        return fail(DAWN_ERR_INVALID, "dimensions must be %d (src/search/vector.rs:26), got %u",
+                    DAWN_DIMENSIONS, o.dimensions);
+    if (o.metric != DAWN_METRIC_IP) return fail(DAWN_ERR_INVALID, "only MetricKind::IP is supported");
+    if (o.scalar != DAWN_SCALAR_F16)
+        return fail(DAWN_ERR_INVALID, "only DAWN_SCALAR_F16 storage is built in this version");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(DAWN_ERR_CUDA, "no CUDA device available (%s); libdawn_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (o.device < 0 || o.device >= n_dev)
+        return fail(DAWN_ERR_INVALID, "device %d out of range (found %d devices)", o.device, n_dev);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, o.device);
+    if (e != cudaSuccess) return fail(DAWN_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(DAWN_ERR_CUDA, "device %d is sm_%d%d; libdawn_b200 is built for sm_100a only", o.device,
+                    prop.major, prop.minor);
+    dawn_index *idx = new (std::nothrow) dawn_index();
+    if (!idx) return fail(DAWN_ERR_INTERNAL, "out of host memory");
+    idx->device = o.device;
+    idx->sm_count = prop.multiProcessorCount;
+    int rc = DAWN_OK;
+    do {
+        if ((e = cudaSetDevice(o.device)) != cudaSuccess) break;
+        if ((e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaMallocHost(&idx->h_stage, kStageRowsHost * kDim * sizeof(float))) != cudaSuccess) break;
+        if ((e = cudaMallocHost(&idx->h_stage_labels, kStageRowsHost * sizeof(uint64_t))) != cudaSuccess) break;
+        if ((e = cudaMalloc(&idx->d_stage, kStageRowsHost * kDim * sizeof(float))) != cudaSuccess) break;
+        if ((e = cudaMallocHost(&idx->h_word, 64)) != cudaSuccess) break;
+    } while (0);
+    if (e != cudaSuccess) {
+        rc = fail(DAWN_ERR_CUDA, "index setup failed: %s", cudaGetErrorString(e));
+        dawn_index_free(idx);
+        return rc;
+    }
+    if (o.capacity > 0) {
+        rc = grow_physical(idx, o.capacity);
+        if (rc != DAWN_OK) {
+            dawn_index_free(idx);
+            return rc;
+        }
+        idx->capacity = o.capacity;
+    }
+    *out = idx;
+    return DAWN_OK;
+}
+
+void dawn_index_free(dawn_index *idx) {
+    if (!idx) return;
+    cudaSetDevice(idx->device);
+    if (idx->stream) cudaStreamSynchronize(idx->stream);
+    for (auto &p : idx->pending) idx->free_events.push_back(p);
+    for (auto &p : idx->free_events) {
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    cudaFree(idx->corpus);
+    cudaFree(idx->labels);
+    cudaFree(idx->d_stage);
+    cudaFreeHost(idx->h_stage);
+    cudaFreeHost(idx->h_stage_labels);
+    cudaFree(idx->d_queries);
+    cudaFreeHost(idx->h_queries);
+    cudaFree(idx->d_labels_out);
+    cudaFreeHost(idx->h_labels_out);
+    cudaFree(idx->d_dist_out);
+    cudaFreeHost(idx->h_dist_out);
+    cudaFree(idx->d_counts);
+    cudaFreeHost(idx->h_counts);
+    cudaFree(idx->d_flags);
+    cudaFreeHost(idx->h_flags);
+    cudaFree(idx->d_partials);
+    cudaFree(idx->d_counters);
+    cudaFreeHost(idx->h_word);
+    if (idx->stream) cudaStreamDestroy(idx->stream);
+    cudaGetLastError();
+    delete idx;
+}
+
+int dawn_index_reserve(dawn_index *idx, size_t n) {
+    int rc = check_alive(idx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if (n <= idx->capacity) return DAWN_OK;
+    rc = grow_physical(idx, n);
+    if (rc) return rc;
+    idx->capacity = n;
+    return DAWN_OK;
+}
+
+int dawn_index_add_batch(dawn_index *idx, const uint64_t *labels, const float *vectors, size_t n) {
+    int rc = check_alive(idx);
+    if (rc) return rc;
+    if (n == 0) return DAWN_OK;
+    if (!labels || !vectors) return fail(DAWN_ERR_INVALID, "labels / vectors is null");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if (idx->size + idx->staged + n > idx->capacity)
+        return fail(DAWN_ERR_CAPACITY, "add of %zu vectors exceeds capacity %zu (size %zu): reserve first", n,
+                    idx->capacity, idx->size + idx->staged);
+    size_t done = 0;
+    while (done < n) {
+        size_t room = kStageRowsHost - idx->staged;
+        size_t take = n - done < room ? n - done : room;
+        memcpy(idx->h_stage + idx->staged * kDim, vectors + done * kDim, take * kDim * sizeof(float));
+        memcpy(idx->h_stage_labels + idx->staged, labels + done, take * sizeof(uint64_t));
+        idx->staged += take;
+        done += take;
+        if (idx->staged == kStageRowsHost) {
+            rc = flush_staged(idx);
+            if (rc) return rc;
+        }
+    }
+    return DAWN_OK;
+}
+
+int dawn_index_add(dawn_index *idx, uint64_t label, const float *vector384) {
+    return dawn_index_add_batch(idx, &label, vector384, 1);
+}
+
+int dawn_index_add_synthetic(dawn_index *idx, uint64_t seed, uint64_t first_row, size_t n) {
+    int rc = check_alive(idx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    rc = flush_staged(idx);
+    if (rc) return rc;
+    if (idx->size + n > idx->capacity)
+        return fail(DAWN_ERR_CAPACITY, "add of %zu vectors exceeds capacity %zu (size %zu): reserve first", n,
+                    idx->capacity, idx->size);
+    CK(idx, launch_synth_f16(idx->corpus + idx->size * kDim, seed, first_row, n, idx->stream));
+    idx->prof.kernel_launches++;
+    // labels = first_row + i + 1, written by a tiny host-free path: reuse the staging buffer
+    size_t done = 0;
+    while (done < n) {
+        size_t take = n - done < kStageRowsHost ? n - done : kStageRowsHost;
+        for (size_t i = 0; i < take; i++) idx->h_stage_labels[i] = first_row + done + i + 1;
+        CK(idx, cudaMemcpyAsync(idx->labels + idx->size + done, idx->h_stage_labels, take * sizeof(uint64_t),
+                                cudaMemcpyHostToDevice, idx->stream));
+        CK(idx, cudaStreamSynchronize(idx->stream));
+        done += take;
+    }
+    CK(idx, cudaStreamSynchronize(idx->stream));
+    idx->size += n;
+    return DAWN_OK;
+}
+
+int dawn_index_search_batch(dawn_index *idx, const float *queries, size_t batch, size_t k,
+                            uint64_t *labels_out, float *distances_out, size_t *counts_out) {
+    int rc = check_alive(idx);
+    if (rc) return rc;
+    if (batch == 0) return DAWN_OK;
+    if (!queries || !counts_out) return fail(DAWN_ERR_INVALID, "queries / counts_out is null");
+    if (k > DAWN_MAX_K) return fail(DAWN_ERR_INVALID, "k = %zu exceeds DAWN_MAX_K = %d", k, DAWN_MAX_K);
+    if (k > 0 && (!labels_out || !distances_out)) return fail(DAWN_ERR_INVALID, "output buffer is null");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    rc = flush_staged(idx);
+    if (rc) return rc;
+    if (k == 0 || idx->size == 0) {
+        for (size_t b = 0; b < batch; b++) counts_out[b] = 0;
+        return DAWN_OK;
+    }
+    rc = ensure_query_ws(idx, batch, k);
+    if (rc) return rc;
+    cudaStream_t s = idx->stream;
+    memcpy(idx->h_queries, queries, batch * kDim * sizeof(float));
+    CK(idx, cudaMemcpyAsync(idx->d_queries, idx->h_queries, batch * kDim * sizeof(float), cudaMemcpyHostToDevice, s));
+    int kprime = choose_kprime(k);
+    rc = search_enqueue(idx, idx->d_queries, batch, k, kprime, idx->d_labels_out, idx->d_dist_out, idx->d_counts,
+                        idx->d_flags, s);
+    if (rc) return rc;
+    CK(idx, cudaMemcpyAsync(idx->h_labels_out, idx->d_labels_out, batch * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CK(idx, cudaMemcpyAsync(idx->h_dist_out, idx->d_dist_out, batch * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(idx, cudaMemcpyAsync(idx->h_counts, idx->d_counts, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(idx, cudaMemcpyAsync(idx->h_flags, idx->d_flags, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(idx, cudaMemcpyAsync(idx->h_word, idx->d_counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(idx, cudaStreamSynchronize(s));
+    if (idx->h_word[0] != 0) return fail(DAWN_ERR_INTERNAL, "scan kernel reported status 0x%x", idx->h_word[0]);
+    memcpy(labels_out, idx->h_labels_out, batch * k * sizeof(uint64_t));
+    memcpy(distances_out, idx->h_dist_out, batch * k * sizeof(float));
+    for (size_t b = 0; b < batch; b++) counts_out[b] = idx->h_counts[b];
+
+    // Exactness certificate not met (near-ties deeper than the slack): re-run those queries
+    // with the longest candidate list.
+    if (kprime < kMaxCand) {
+        for (size_t b = 0; b < batch; b++) {
+            if (idx->h_flags[b] & 1u) continue;
+            idx->prof.escalations++;
+            rc = search_enqueue(idx, idx->d_queries + b * kDim, 1, k, kMaxCand, idx->d_labels_out, idx->d_dist_out,
+                                idx->d_counts, idx->d_flags, s);
+            if (rc) return rc;
+            CK(idx, cudaMemcpyAsync(idx->h_labels_out, idx->d_labels_out, k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            CK(idx, cudaMemcpyAsync(idx->h_dist_out, idx->d_dist_out, k * sizeof(float), cudaMemcpyDeviceToHost, s));
+            CK(idx, cudaMemcpyAsync(idx->h_counts, idx->d_counts, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CK(idx, cudaMemcpyAsync(idx->h_word + 1, idx->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CK(idx, cudaStreamSynchronize(s));
+            memcpy(labels_out + b * k, idx->h_labels_out, k * sizeof(uint64_t));
+            memcpy(distances_out + b * k, idx->h_dist_out, k * sizeof(float));
+            counts_out[b] = idx->h_counts[0];
+            if (!(idx->h_word[1] & 1u)) idx->prof.uncertified++;
+        }
+    } else {
+        for (size_t b = 0; b < batch; b++)
+            if (!(idx->h_flags[b] & 1u)) idx->prof.uncertified++;
+    }
+    return DAWN_OK;
+}
+
+int dawn_index_search(dawn_index *idx, const float *query384, size_t k, uint64_t *labels_out,
+                      float *distances_out, size_t *count_out) {
+    return dawn_index_search_batch(idx, query384, 1, k, labels_out, distances_out, count_out);
+}
+
+int dawn_index_search_device(dawn_index *idx, const float *d_queries, size_t batch, size_t k,
+                             uint64_t *d_labels_out, float *d_distances_out, uint32_t *d_counts_out,
+                             uint32_t *d_flags_out, void *stream) {
+    int rc = check_alive(idx);
+    if (rc) return rc;
+    if (batch == 0) return DAWN_OK;
+    if (!d_queries || !d_labels_out || !d_distances_out || !d_counts_out || !d_flags_out)
+        return fail(DAWN_ERR_INVALID, "null device pointer");
+    if (k == 0 || k > DAWN_MAX_K) return fail(DAWN_ERR_INVALID, "k = %zu out of range 1..%d", k, DAWN_MAX_K);
+    std::lock_guard<std::mutex> lk(idx->mu);
+    rc = flush_staged(idx);
+    if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : idx->stream;
+    if (idx->size == 0) {
+        CK(idx, cudaMemsetAsync(d_counts_out, 0, batch * sizeof(uint32_t), s));
+        CK(idx, cudaMemsetAsync(d_flags_out, 0, batch * sizeof(uint32_t), s));
+        return DAWN_OK;
+    }
+    return search_enqueue(idx, d_queries, batch, k, choose_kprime(k), d_labels_out, d_distances_out, d_counts_out,
+                          d_flags_out, s);
+}
+
+size_t dawn_index_size(const dawn_index *idx) { return idx ? idx->size + idx->staged : 0; }
+size_t dawn_index_capacity(const dawn_index *idx) { return idx ? idx->capacity : 0; }
+size_t dawn_index_dimensions(const dawn_index *idx) { return idx ? DAWN_DIMENSIONS : 0; }
+
+int dawn_index_get(dawn_index *idx, uint64_t label, float *vector384_out) {
+    int rc = check_alive(idx);
+    if (rc) return rc;
+    if (!vector384_out) return fail(DAWN_ERR_INVALID, "output is null");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    rc = flush_staged(idx);
+    if (rc) return rc;
+    if (idx->size == 0) return fail(DAWN_ERR_INVALID, "label %llu not found", (unsigned long long)label);
+    rc = ensure_query_ws(idx, 1, 1);
+    if (rc) return rc;
+    cudaStream_t s = idx->stream;
+    CK(idx, launch_find_label(idx->labels, idx->size, label, idx->d_counts, s));
+    idx->prof.kernel_launches++;
+    CK(idx, cudaMemcpyAsync(idx->h_counts, idx->d_counts, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(idx, cudaStreamSynchronize(s));
+    if (idx->h_counts[0] == kNoRow) return fail(DAWN_ERR_INVALID, "label %llu not found", (unsigned long long)label);
+    CK(idx, launch_gather_f32(idx->corpus, idx->d_counts, 1, idx->d_queries, s));
+    idx->prof.kernel_launches++;
+    CK(idx, cudaMemcpyAsync(idx->h_queries, idx->d_queries, kDim * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(idx, cudaStreamSynchronize(s));
+    memcpy(vector384_out, idx->h_queries, kDim * sizeof(float));
+    return DAWN_OK;
+}
+
+// ---- save / load: header, labels, fp16 rows (raw device layout) -------------------------
+struct SaveHeader {
+    char magic[8];  // "DAWNB200"
+    uint32_t version, scalar, dims, reserved;
+    uint64_t size;
+};
+
+int dawn_index_save(dawn_index *idx, const char *path) {
+    int rc = check_alive(idx);
+    if (rc) return rc;
+    if (!path) return fail(DAWN_ERR_INVALID, "path is null");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    rc = flush_staged(idx);
+    if (rc) return rc;
+    std::string tmp = std::string(path) + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(DAWN_ERR_IO, "cannot open %s for writing", tmp.c_str());
+    SaveHeader h{};
+    memcpy(h.magic, "DAWNB200", 8);
+    h.version = 1;
+    h.scalar = DAWN_SCALAR_F16;
+    h.dims = kDim;
+    h.size = idx->size;
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    // stream device memory out through the pinned staging buffer
+    const size_t buf_bytes = kStageRowsHost * kDim * sizeof(float);
+    auto dump = [&](const void *dptr, size_t bytes) -> int {
+        size_t off = 0;
+        while (ok && off < bytes) {
+            size_t take = bytes - off < buf_bytes ? bytes - off : buf_bytes;
+            CK(idx, cudaMemcpyAsync(idx->h_stage, (const char *)dptr + off, take, cudaMemcpyDeviceToHost, idx->stream));
+            CK(idx, cudaStreamSynchronize(idx->stream));
+            ok = fwrite(idx->h_stage, 1, take, f) == take;
+            off += take;
+        }
+        return DAWN_OK;
+    };
+    rc = dump(idx->labels, idx->size * sizeof(uint64_t));
+    if (rc == DAWN_OK) rc = dump(idx->corpus, idx->size * kRowBytesF16);
+    ok = (fclose(f) == 0) && ok;
+    if (rc != DAWN_OK || !ok) {
+        remove(tmp.c_str());
+        return rc != DAWN_OK ? rc : fail(DAWN_ERR_IO, "short write to %s", tmp.c_str());
+    }
+    if (rename(tmp.c_str(), path) != 0) {
+        remove(tmp.c_str());
+        return fail(DAWN_ERR_IO, "cannot rename %s to %s", tmp.c_str(), path);
+    }
+    return DAWN_OK;
+}
+
+int dawn_index_load(dawn_index *idx, const char *path) {
+    int rc = check_alive(idx);
+    if (rc) return rc;
+    if (!path) return fail(DAWN_ERR_INVALID, "path is null");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(DAWN_ERR_IO, "cannot open %s", path);
+    SaveHeader h{};
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "DAWNB200", 8) != 0 || h.version != 1 ||
+        h.scalar != DAWN_SCALAR_F16 || h.dims != kDim) {
+        fclose(f);
+        return fail(DAWN_ERR_IO, "%s is not a libdawn_b200 fp16 index file", path);
+    }
+    // validate the length before touching the index, so a failed load leaves it unchanged
+    // (the reference falls back to a rebuild when load fails, search_provider.rs:115-116)
+    fseek(f, 0, SEEK_END);
+    long long flen = ftell(f);
+    long long want = (long long)sizeof h + (long long)h.size * (8 + kRowBytesF16);
+    if (flen != want) {
+        fclose(f);
+        return fail(DAWN_ERR_IO, "%s is truncated (%lld bytes, expected %lld)", path, flen, want);
+    }
+    fseek(f, sizeof h, SEEK_SET);
+    rc = grow_physical(idx, h.size);
+    if (rc) {
+        fclose(f);
+        return rc;
+    }
+    const size_t buf_bytes = kStageRowsHost * kDim * sizeof(float);
+    bool ok = true;
+    auto slurp = [&](void *dptr, size_t bytes) -> int {
+        size_t off = 0;
+        while (ok && off < bytes) {
+            size_t take = bytes - off < buf_bytes ? bytes - off : buf_bytes;
+            ok = fread(idx->h_stage, 1, take, f) == take;
+            if (!ok) break;
+            CK(idx, cudaMemcpyAsync((char *)dptr + off, idx->h_stage, take, cudaMemcpyHostToDevice, idx->stream));
+            CK(idx, cudaStreamSynchronize(idx->stream));
+            off += take;
+        }
+        return DAWN_OK;
+    };
+    idx->staged = 0;
+    idx->size = 0;  // from here on the old contents are gone
+    rc = slurp(idx->labels, h.size * sizeof(uint64_t));
+    if (rc == DAWN_OK) rc = slurp(idx->corpus, h.size * kRowBytesF16);
+    fclose(f);
+    if (rc != DAWN_OK) return rc;
+    if (!ok) return fail(DAWN_ERR_IO, "read error on %s", path);
+    idx->size = h.size;
+    if (idx->capacity < idx->size) idx->capacity = idx->size;
+    return DAWN_OK;
+}
+
+int dawn_index_set_profiling(dawn_index *idx, int enable) {
+    int rc = check_alive(idx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    drain_events(idx);
+    idx->profiling = enable != 0;
+    return DAWN_OK;
+}
+
+int dawn_index_get_profile(dawn_index *idx, dawn_profile *out, int reset) {
+    int rc = check_alive(idx);
+    if (rc) return rc;
+    if (!out) return fail(DAWN_ERR_INVALID, "out is null");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    drain_events(idx);
+    *out = idx->prof;
+    if (reset) idx->prof = dawn_profile{};
+    return DAWN_OK;
+}
+
+int dawn_merge_results_device(int device, const uint64_t *d_labels, const float *d_distances,
+                              const uint32_t *d_counts, size_t n_lists, size_t batch, size_t k,
+                              uint64_t *d_labels_out, float *d_distances_out, uint32_t *d_counts_out,
+                              void *stream) {
+    if (!d_labels || !d_distances || !d_counts || !d_labels_out || !d_distances_out || !d_counts_out)
+        return fail(DAWN_ERR_INVALID, "null device pointer");
+    if (k == 0 || k > DAWN_MAX_K || n_lists == 0 || n_lists * k > 1024)
+        return fail(DAWN_ERR_INVALID, "merge shape out of range (n_lists=%zu k=%zu; n_lists*k must be <= 1024)",
+                    n_lists, k);
+    if (batch == 0) return DAWN_OK;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess)
+        e = launch_merge_results(d_labels, d_distances, d_counts, (int)n_lists, (int)batch, (int)k, d_labels_out,
+                                 d_distances_out, d_counts_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(DAWN_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(e));
+    return DAWN_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ small kernels
+
+namespace {
+
+// K7 (device side of the sharded search): merge n_lists sorted result lists per query.
+// Order: distance ascending, label ascending, then list index (strict).  One CTA per query,
+// one thread per input entry; rank = position in own list + binary-searched counts in the others.
+__global__ void __launch_bounds__(1024) merge_results_kernel(
+    const uint64_t *__restrict__ labels, const float *__restrict__ dist, const uint32_t *__restrict__ counts,
+    int n_lists, int batch, int k, uint64_t *__restrict__ labels_out, float *__restrict__ dist_out,
+    uint32_t *__restrict__ counts_out) {
+    __shared__ uint64_t s_lab[1024];
+    __shared__ float s_dist[1024];
+    __shared__ int s_cnt[64];
+    const int qi = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int total = n_lists * k;
+    if (tid < n_lists) s_cnt[tid] = min((int)counts[(size_t)tid * batch + qi], k);
+    if (tid < total) {
+        const int l = tid / k, p = tid % k;
+        s_lab[tid] = labels[((size_t)l * batch + qi) * k + p];
+        s_dist[tid] = dist[((size_t)l * batch + qi) * k + p];
+    }
+    __syncthreads();
+    int all = 0;
+    for (int l = 0; l < n_lists; l++) all += s_cnt[l];
+    if (tid < total) {
+        const int l = tid / k, p = tid % k;
+        if (p < s_cnt[l]) {
+            const float d = s_dist[tid];
+            const uint64_t lab = s_lab[tid];
+            int rank = p;
+            for (int o = 0; o < n_lists; o++) {
+                if (o == l) continue;
+                int lo = 0, hi = s_cnt[o];
+                while (lo < hi) {  // count entries of list o that come before (d, lab, l)
+                    const int mid = (lo + hi) >> 1;
+                    const float od = s_dist[o * k + mid];
+                    const uint64_t ol = s_lab[o * k + mid];
+                    const bool before = od < d || (od == d && (ol < lab || (ol == lab && o < l)));
+                    if (before) lo = mid + 1;
+                    else hi = mid;
+                }
+                rank += lo;
+            }
+            if (rank < k) {
+                labels_out[(size_t)qi * k + rank] = lab;
+                dist_out[(size_t)qi * k + rank] = d;
+            }
+        }
+    }
+    if (tid == 0) counts_out[qi] = (uint32_t)min(all, k);
+}
+
+__global__ void __launch_bounds__(256) find_label_kernel(const uint64_t *__restrict__ labels, size_t n,
+                                                         uint64_t label, uint32_t *__restrict__ row_out) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (labels[i] == label) atomicMin(row_out, (uint32_t)i);
+}
+
+cudaError_t launch_merge_results(const uint64_t *labels, const float *dist, const uint32_t *counts, int n_lists,
+                                 int batch, int k, uint64_t *labels_out, float *dist_out, uint32_t *counts_out,
+                                 cudaStream_t s) {
+    if (n_lists > 64) return cudaErrorInvalidValue;
+    merge_results_kernel<<<batch, 1024, 0, s>>>(labels, dist, counts, n_lists, batch, k, labels_out, dist_out,
+                                                counts_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_find_label(const uint64_t *labels, size_t n, uint64_t label, uint32_t *row_out,
+                              cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(row_out, 0xFF, sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    find_label_kernel<<<(unsigned)blocks, 256, 0, s>>>(labels, n, label, row_out);
+    return cudaGetLastError();
+}
+
+}  // namespace

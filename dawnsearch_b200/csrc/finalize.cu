@@ -1,0 +1,192 @@
+// finalize.cu -- K5 + K6: merge the per-CTA candidate lists, re-score the survivors in the
+// reference's order of summation, and emit the final (label, distance) pairs.
+//
+// K5 is the device counterpart of BestResults (/root/reference/src/search/best_results.rs:44-79):
+// keep the k best of many partial result sets.  Unlike BestResults the order is total and
+// independent of arrival: (score desc, label asc, row asc).
+// K6 recomputes each surviving candidate's score exactly like the reference's scalar code
+// (src/search/vector.rs:128-134: `result += a[i]*b[i]` in index order, one f32 rounding for
+// the multiply and one for the add), so the scores, the final order and the distances
+// (1 - score) are bit-identical to oracle/dawn_oracle.c:dawn_oracle_search_f16.
+// The scan only has to deliver a superset: k' = k + slack candidates whose approximate
+// scores are within `eps` of the exact ones.  The certificate bit says the slack was
+// provably enough: every row the scan dropped scored <= the weakest kept candidate, which
+// is more than eps below the k-th exact score.
+//
+// One CTA per query; latency-bound (a few microseconds), negligible bytes.
+#include "dawn_common.cuh"
+
+namespace dawn {
+
+namespace {
+
+constexpr int kFinThreads = 1024;
+constexpr int kFinCapEntries = 4096;  // 64 KB of candidates in shared memory per round
+constexpr int kFinItems = kFinCapEntries / kFinThreads;
+
+struct FinSmem {
+    alignas(16) Cand s[kFinCapEntries];
+    alignas(16) float q[kDim];
+    float scan_score[kMaxCand];
+    uint32_t n_valid;
+    float kth_dist;
+};
+
+__device__ __forceinline__ bool dist_before(const Cand &a, const Cand &b) {
+    if (a.score != b.score) return a.score < b.score;
+    if (a.label != b.label) return a.label < b.label;
+    return a.row < b.row;
+}
+
+// S holds n_lists sorted lists of length kp (sentinel padded); tree-merge them into list 0.
+// Each entry finds its rank in the union of its pair by binary search in the partner list.
+__device__ void merge_lists(Cand *S, int n_lists, int kp, int tid) {
+    for (int stride = 1; stride < n_lists; stride <<= 1) {
+        const int n_pairs = (n_lists - stride + 2 * stride - 1) / (2 * stride);
+        const int n_items = n_pairs * 2 * kp;
+        Cand e[kFinItems];
+        int dst[kFinItems];
+#pragma unroll
+        for (int it = 0; it < kFinItems; it++) {
+            const int i = tid + it * kFinThreads;
+            dst[it] = -1;
+            if (i < n_items) {
+                const int pair = i / (2 * kp);
+                const int within = i % (2 * kp);
+                const int a = pair * 2 * stride;
+                const bool in_a = within < kp;
+                const int p = in_a ? within : within - kp;
+                const Cand *own = S + (size_t)(in_a ? a : a + stride) * kp;
+                const Cand *other = S + (size_t)(in_a ? a + stride : a) * kp;
+                e[it] = own[p];
+                int lo = 0, hi = kp;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (cand_better(other[mid], e[it])) lo = mid + 1;
+                    else hi = mid;
+                }
+                const int rank = p + lo;
+                if (rank < kp) dst[it] = a * kp + rank;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < kFinItems; it++)
+            if (dst[it] >= 0) S[dst[it]] = e[it];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kFinThreads, 1)
+finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ queries,
+                const Cand *__restrict__ partials, int n_lists, int kp, int k, float eps,
+                uint64_t *__restrict__ labels_out, float *__restrict__ distances_out,
+                uint32_t *__restrict__ counts_out, uint32_t *__restrict__ flags_out) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    FinSmem &sm = *reinterpret_cast<FinSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int qi = blockIdx.x;
+    const Cand *lists = partials + (size_t)qi * n_lists * kp;
+
+    for (int c = tid; c < kDim; c += kFinThreads) sm.q[c] = queries[(size_t)qi * kDim + c];
+
+    // ---- K5: streaming tree merge, cap_lists lists per round, list 0 is the running result
+    const int cap_lists = kFinCapEntries / kp;
+    int next = 0;
+    bool first = true;
+    while (next < n_lists || first) {
+        const int keep = first ? 0 : 1;
+        const int take = min(cap_lists - keep, n_lists - next);
+        for (int i = tid; i < take * kp; i += kFinThreads)
+            sm.s[keep * kp + i] = lists[(size_t)next * kp + i];
+        __syncthreads();
+        merge_lists(sm.s, keep + take, kp, tid);
+        next += take;
+        first = false;
+    }
+    __syncthreads();
+
+    // ---- K6: exact re-score, one candidate per thread, sequential f32 mul + add
+    Cand mine = empty_cand();
+    if (tid < kp) {
+        mine = sm.s[tid];
+        sm.scan_score[tid] = mine.score;
+        if (mine.row != kNoRow) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(corpus + (size_t)mine.row * kDim);
+            float acc = 0.0f;
+#pragma unroll 4
+            for (int c = 0; c < kDim / 8; c++) {
+                const uint4 u = __ldg(rp + c);
+                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 x = __half22float2(h[j]);
+                    acc = __fadd_rn(acc, __fmul_rn(sm.q[c * 8 + 2 * j], x.x));
+                    acc = __fadd_rn(acc, __fmul_rn(sm.q[c * 8 + 2 * j + 1], x.y));
+                }
+            }
+            mine.score = __fsub_rn(1.0f, acc);  // distance, vector.rs:133
+        }
+    }
+    __syncthreads();
+    // From here on Cand::score holds the DISTANCE (smaller is better); empty slots get +inf.
+    if (tid < kp) {
+        if (mine.row == kNoRow) mine.score = __int_as_float(0x7f800000);
+        sm.s[tid] = mine;
+    }
+    __syncthreads();
+
+    // ---- final order: distance asc, label asc, row asc (rank counting over <= 128 entries).
+    // Ordering on the emitted f32 distance (not the score) makes the output self-consistent
+    // and lets sharded results be merged from (label, distance) pairs alone.
+    int rank = 0;
+    const bool valid = tid < kp && mine.row != kNoRow;
+    if (valid) {
+        for (int j = 0; j < kp; j++) rank += dist_before(sm.s[j], mine) ? 1 : 0;
+    }
+    const unsigned n_valid_warp = __popc(__ballot_sync(0xffffffffu, valid));
+    if (tid == 0) sm.n_valid = 0;
+    __syncthreads();
+    if ((tid & 31) == 0 && n_valid_warp) atomicAdd(&sm.n_valid, n_valid_warp);
+    __syncthreads();
+    const int n_valid = (int)sm.n_valid;
+    if (valid && rank < k) {
+        labels_out[(size_t)qi * k + rank] = mine.label;
+        distances_out[(size_t)qi * k + rank] = mine.score;
+        if (rank == k - 1) sm.kth_dist = mine.score;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        counts_out[qi] = (uint32_t)min(k, n_valid);
+        bool certified = true;
+        if (n_valid == kp) {
+            // A row outside the candidate set has scan score <= scan_min, hence exact score
+            // <= scan_min + eps and distance >= 1 - (scan_min + eps); it cannot displace or tie
+            // the k-th result if that bound is strictly above the k-th distance.
+            const float bound = __fsub_rn(1.0f, __fadd_rn(sm.scan_score[kp - 1], eps));
+            certified = bound > sm.kth_dist;
+        }
+        flags_out[qi] = certified ? 1u : 0u;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s) {
+    if (p.nq == 0) return cudaSuccess;
+    if (p.kprime < 1 || p.kprime > kMaxCand || p.k < 1 || p.k > p.kprime) return cudaErrorInvalidValue;
+    static bool configured = false;
+    const size_t smem = sizeof(FinSmem);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    finalize_kernel<<<p.nq, kFinThreads, smem, s>>>(p.corpus, p.queries, p.partials, p.n_lists,
+                                                   p.kprime, p.k, p.eps, p.labels_out, p.distances_out,
+                                                   p.counts_out, p.flags_out);
+    return cudaGetLastError();
+}
+
+}  // namespace dawn

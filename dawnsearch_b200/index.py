@@ -1,0 +1,268 @@
+"""ctypes binding of libdawn_b200.so with the method names of `usearch::ffi::Index`.
+
+The reference drives its index through the `usearch::ffi` cxx bridge
+(/root/reference/src/search/search_provider.rs:32-42,102,115-117,133,149,178,214,246,280-284):
+
+    new_index(&IndexOptions) -> Index
+    index.reserve(n) / add(label, &[f32]) / search(&[f32], k) -> Matches{labels, distances}
+    index.size() / capacity() / dimensions() / save(path) / load(path) / view(path)
+
+This module exposes the same names over the C ABI in include/dawn_index.h so that the
+parity tests read like calls into the reference.  Errors surface as `DawnError`
+(the cxx bridge maps C++ exceptions to `Result::Err`).
+
+There is no CPU fallback: importing works anywhere, but creating an index without the
+built library or without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+EM_LEN = 384  # src/search/vector.rs:26
+MAX_K = 120
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdawn_b200.so")
+
+_vp = C.c_void_p
+
+
+class DawnError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libdawn_b200 error {code}: {message}")
+        self.code = code
+
+
+class MetricKind:  # usearch::ffi::MetricKind (search_provider.rs:37)
+    IP = 0
+
+
+class ScalarKind:  # usearch::ffi::ScalarKind (search_provider.rs:38); storage precision
+    F16 = 0
+    I8 = 1
+
+
+class _Options(C.Structure):
+    _fields_ = [
+        ("dimensions", C.c_uint32),
+        ("metric", C.c_uint32),
+        ("scalar", C.c_uint32),
+        ("device", C.c_int32),
+        ("capacity", C.c_uint64),
+        ("flags", C.c_uint32),
+        ("reserved_", C.c_uint32),
+    ]
+
+
+class Profile(C.Structure):
+    _fields_ = [
+        ("scan_launches", C.c_uint64),
+        ("scan_ms", C.c_double),
+        ("finalize_launches", C.c_uint64),
+        ("finalize_ms", C.c_double),
+        ("queries", C.c_uint64),
+        ("uncertified", C.c_uint64),
+        ("escalations", C.c_uint64),
+        ("kernel_launches", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+@dataclass
+class IndexOptions:
+    """usearch::ffi::IndexOptions as the reference fills it (search_provider.rs:35-42).
+    connectivity / expansion_* are accepted and ignored: the search is exact."""
+
+    dimensions: int = EM_LEN
+    metric: int = MetricKind.IP
+    quantization: int = ScalarKind.F16
+    connectivity: int = 0
+    expansion_add: int = 0
+    expansion_search: int = 0
+    device: int = 0
+    capacity: int = 0
+
+
+@dataclass
+class Matches:
+    """usearch::ffi::Matches (search_provider.rs:221): labels and distances, ascending."""
+
+    labels: np.ndarray
+    distances: np.ndarray
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libdawn_b200.so; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DawnError(-5, f"{LIB_PATH} is missing: run `make -C dawnsearch_b200/csrc` "
+                            "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.dawn_last_error.restype = C.c_char_p
+    L.dawn_version.restype = C.c_char_p
+    L.dawn_index_create.argtypes = [C.POINTER(_Options), C.POINTER(_vp)]
+    L.dawn_index_free.argtypes = [_vp]
+    L.dawn_index_free.restype = None
+    L.dawn_index_reserve.argtypes = [_vp, C.c_size_t]
+    L.dawn_index_add.argtypes = [_vp, C.c_uint64, _vp]
+    L.dawn_index_add_batch.argtypes = [_vp, _vp, _vp, C.c_size_t]
+    L.dawn_index_search.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp, _vp]
+    L.dawn_index_search_batch.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp]
+    L.dawn_index_search_device.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _vp]
+    L.dawn_merge_results_device.argtypes = [C.c_int, _vp, _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t,
+                                            _vp, _vp, _vp, _vp]
+    for name in ("dawn_index_size", "dawn_index_capacity", "dawn_index_dimensions"):
+        getattr(L, name).argtypes = [_vp]
+        getattr(L, name).restype = C.c_size_t
+    L.dawn_index_save.argtypes = [_vp, C.c_char_p]
+    L.dawn_index_load.argtypes = [_vp, C.c_char_p]
+    L.dawn_index_get.argtypes = [_vp, C.c_uint64, _vp]
+    L.dawn_index_add_synthetic.argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_size_t]
+    L.dawn_index_set_profiling.argtypes = [_vp, C.c_int]
+    L.dawn_index_get_profile.argtypes = [_vp, C.POINTER(Profile), C.c_int]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise DawnError(rc, load_library().dawn_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_vp)
+
+
+class Index:
+    """Device-resident exact index; method names follow usearch::ffi::Index."""
+
+    def __init__(self, options: IndexOptions):
+        L = load_library()
+        if options.quantization not in (ScalarKind.F16,):
+            raise DawnError(-1, "only ScalarKind.F16 storage is built in this version")
+        o = _Options(options.dimensions, options.metric, options.quantization, options.device,
+                     options.capacity, 0, 0)
+        h = _vp()
+        _check(L.dawn_index_create(C.byref(o), C.byref(h)))
+        self._h = h
+        self._L = L
+        self.device = options.device
+
+    # -- lifetime ------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dawn_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- usearch::ffi::Index surface --------------------------------------------------
+    def reserve(self, capacity: int) -> None:  # search_provider.rs:133,282
+        _check(self._L.dawn_index_reserve(self._h, capacity))
+
+    def add(self, label: int, vector) -> None:  # search_provider.rs:149,284
+        v = np.ascontiguousarray(vector, dtype=np.float32)
+        if v.shape != (EM_LEN,):
+            raise DawnError(-1, f"vector must have {EM_LEN} dimensions, got {v.shape}")
+        _check(self._L.dawn_index_add(self._h, int(label), _ptr(v)))
+
+    def add_batch(self, labels, vectors) -> None:
+        lab = np.ascontiguousarray(labels, dtype=np.uint64)
+        v = np.ascontiguousarray(vectors, dtype=np.float32).reshape(-1, EM_LEN)
+        if lab.shape[0] != v.shape[0]:
+            raise DawnError(-1, "labels and vectors differ in length")
+        _check(self._L.dawn_index_add_batch(self._h, _ptr(lab), _ptr(v), v.shape[0]))
+
+    def search(self, query, count: int) -> Matches:  # search_provider.rs:214
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        if q.shape != (EM_LEN,):
+            raise DawnError(-1, f"query must have {EM_LEN} dimensions, got {q.shape}")
+        labels = np.zeros(max(count, 1), dtype=np.uint64)
+        dist = np.zeros(max(count, 1), dtype=np.float32)
+        n = C.c_size_t(0)
+        _check(self._L.dawn_index_search(self._h, _ptr(q), count, _ptr(labels), _ptr(dist), C.byref(n)))
+        return Matches(labels[: n.value].copy(), dist[: n.value].copy())
+
+    def search_batch(self, queries, count: int):
+        """-> (labels[B,count], distances[B,count], counts[B]); rows valid up to counts[b]."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, EM_LEN)
+        b = q.shape[0]
+        labels = np.zeros((b, max(count, 1)), dtype=np.uint64)
+        dist = np.zeros((b, max(count, 1)), dtype=np.float32)
+        counts = np.zeros(b, dtype=np.uint64)
+        _check(self._L.dawn_index_search_batch(self._h, _ptr(q), b, count, _ptr(labels), _ptr(dist),
+                                               _ptr(counts)))
+        return labels, dist, counts.astype(np.int64)
+
+    def size(self) -> int:  # search_provider.rs:246,280
+        return int(self._L.dawn_index_size(self._h))
+
+    def capacity(self) -> int:  # search_provider.rs:280
+        return int(self._L.dawn_index_capacity(self._h))
+
+    def dimensions(self) -> int:
+        return int(self._L.dawn_index_dimensions(self._h))
+
+    def save(self, path: str) -> None:  # search_provider.rs:117,178
+        _check(self._L.dawn_index_save(self._h, os.fsencode(path)))
+
+    def load(self, path: str) -> None:  # search_provider.rs:115
+        _check(self._L.dawn_index_load(self._h, os.fsencode(path)))
+
+    view = load  # examples_old/search_usearch.rs:47 (a device index is always a copy)
+
+    # -- additions ---------------------------------------------------------------------
+    def get(self, label: int) -> np.ndarray:  # SearchProvider::embedding_for_page, :183-195
+        out = np.zeros(EM_LEN, dtype=np.float32)
+        _check(self._L.dawn_index_get(self._h, int(label), _ptr(out)))
+        return out
+
+    def add_synthetic(self, seed: int, first_row: int, n: int) -> None:
+        _check(self._L.dawn_index_add_synthetic(self._h, seed, first_row, n))
+
+    def search_device(self, d_queries: int, batch: int, count: int, d_labels: int, d_dist: int,
+                      d_counts: int, d_flags: int, stream: int = 0) -> None:
+        """Raw device-pointer entry point (ints are CUDA device addresses); only enqueues."""
+        _check(self._L.dawn_index_search_device(self._h, d_queries, batch, count, d_labels, d_dist,
+                                                d_counts, d_flags, stream))
+
+    def set_profiling(self, enable: bool) -> None:
+        _check(self._L.dawn_index_set_profiling(self._h, int(enable)))
+
+    def profile(self, reset: bool = False) -> dict:
+        p = Profile()
+        _check(self._L.dawn_index_get_profile(self._h, C.byref(p), int(reset)))
+        return p.as_dict()
+
+
+def new_index(options: IndexOptions | None = None) -> Index:
+    """usearch::ffi::new_index (search_provider.rs:102)."""
+    return Index(options or IndexOptions())
+
+
+def merge_results_device(device: int, d_labels: int, d_dist: int, d_counts: int, n_lists: int,
+                         batch: int, k: int, d_labels_out: int, d_dist_out: int, d_counts_out: int,
+                         stream: int = 0) -> None:
+    _check(load_library().dawn_merge_results_device(device, d_labels, d_dist, d_counts, n_lists, batch, k,
+                                                    d_labels_out, d_dist_out, d_counts_out, stream))

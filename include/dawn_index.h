@@ -1,0 +1,153 @@
+/*
+ * dawn_index.h -- C ABI of libdawn_b200.so: a device-resident exact top-k index for
+ * 384-d page embeddings on NVIDIA B200 (sm_100a).
+ *
+ * Drop-in boundary: these entry points are what a Rust FFI layer binds in place of the
+ * `usearch::ffi` cxx bridge that the reference uses today.  Each function names the
+ * reference interface it replaces (paths relative to dawn-search/dawnsearch v0.2.0):
+ *
+ *   reference (usearch::ffi, called from src/search/search_provider.rs)      this header
+ *   ---------------------------------------------------------------------   ----------------------
+ *   new_index(&IndexOptions)              :35-42, :102                       dawn_index_create
+ *   drop(UniquePtr<Index>)                :67                                dawn_index_free
+ *   Index::reserve(usize)                 :133, :282                         dawn_index_reserve
+ *   Index::add(u64, &[f32])               :149, :284                         dawn_index_add / _add_batch
+ *   Index::search(&[f32], usize)->Matches :214, :221                         dawn_index_search / _search_batch
+ *   Index::size() / capacity()            :246, :280                         dawn_index_size / _capacity
+ *   Index::dimensions()                   (IndexOptions.dimensions :36)      dawn_index_dimensions
+ *   Index::save(&str) / load(&str)        :115, :117, :178                   dawn_index_save / _load
+ *   Index::view(&str)  (examples_old/search_usearch.rs:47)                   dawn_index_load
+ *   cxx::Exception -> Result::Err         :102,:117,:133,:149,:214,:284      negative return + dawn_last_error()
+ *
+ * Semantics kept from the reference: distances are "smaller is better" and equal
+ * 1 - dot(query, stored) (src/search/vector.rs:128-134; consumers: src/net/web.rs:330-343,
+ * src/net/udp_service.rs:196-199, src/search/best_results.rs:56); results come back
+ * ascending by distance; labels are caller-supplied u64 page ids (SQLite rowids); fewer
+ * than k results are returned when the index holds fewer than k vectors; the caller checks
+ * that vectors are L2-normalised before calling (search_provider.rs:206,265).
+ * Added on top: the search is exact (not HNSW) over the stored fp16 vectors and ties break
+ * deterministically on the lower label.
+ *
+ * There is NO CPU fallback: every call that needs the GPU fails with DAWN_ERR_CUDA if no
+ * sm_100 device is usable.
+ *
+ * Threading: the reference drives its index from a single thread
+ * (src/bin/dawnsearch.rs:76-78).  Calls on one handle are serialised internally by a mutex;
+ * different handles are independent.  A handle may be used from any thread.
+ */
+#ifndef DAWN_INDEX_H
+#define DAWN_INDEX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAWN_DIMENSIONS 384 /* src/search/vector.rs:26 EM_LEN */
+#define DAWN_MAX_K 120      /* largest k one search call accepts */
+
+enum {
+    DAWN_OK = 0,
+    DAWN_ERR_INVALID = -1,   /* bad argument (null pointer, k out of range, wrong dimension) */
+    DAWN_ERR_CUDA = -2,      /* CUDA failure; sticky: the handle refuses further work */
+    DAWN_ERR_CAPACITY = -3,  /* add beyond reserved capacity (usearch raises the same way) */
+    DAWN_ERR_IO = -4,        /* save / load failed; the index is unchanged */
+    DAWN_ERR_INTERNAL = -5
+};
+
+/* usearch ScalarKind equivalents for the stored corpus (search_provider.rs:38). */
+enum { DAWN_SCALAR_F16 = 0, DAWN_SCALAR_I8 = 1 };
+/* usearch MetricKind::IP (search_provider.rs:37) is the only metric the reference uses. */
+enum { DAWN_METRIC_IP = 0 };
+
+typedef struct dawn_options {
+    uint32_t dimensions; /* must be 384 (0 = default) */
+    uint32_t metric;     /* DAWN_METRIC_IP */
+    uint32_t scalar;     /* DAWN_SCALAR_F16 (DAWN_SCALAR_I8: not in this build) */
+    int32_t device;      /* CUDA device ordinal */
+    uint64_t capacity;   /* vectors to reserve up front (0 = none) */
+    uint32_t flags;      /* reserved, 0 */
+    uint32_t reserved_;
+} dawn_options;
+
+typedef struct dawn_index dawn_index;
+
+/* Per-thread message for the last failing call on this thread ("" if none). */
+const char *dawn_last_error(void);
+/* "libdawn_b200 <version> sm_100a" */
+const char *dawn_version(void);
+
+int dawn_index_create(const dawn_options *opts, dawn_index **out);
+void dawn_index_free(dawn_index *idx);
+
+/* Grow capacity to at least n vectors (never shrinks).  Existing vectors are kept. */
+int dawn_index_reserve(dawn_index *idx, size_t n);
+/* Append one / n labelled f32 vectors (host memory).  Vectors become visible to the next
+ * search.  Fails with DAWN_ERR_CAPACITY when size + n > capacity (the reference grows by
+ * reserve(size+1024) itself, search_provider.rs:280-283). */
+int dawn_index_add(dawn_index *idx, uint64_t label, const float *vector384);
+int dawn_index_add_batch(dawn_index *idx, const uint64_t *labels, const float *vectors, size_t n);
+
+/* Exact top-k for one / `batch` f32 queries in host memory.  Output buffers are caller
+ * allocated: labels[batch*k], distances[batch*k], counts[batch]; row b's results occupy
+ * [b*k, b*k + counts[b]), ascending by distance, ties by ascending label. */
+int dawn_index_search(dawn_index *idx, const float *query384, size_t k, uint64_t *labels_out,
+                      float *distances_out, size_t *count_out);
+int dawn_index_search_batch(dawn_index *idx, const float *queries, size_t batch, size_t k,
+                            uint64_t *labels_out, float *distances_out, size_t *counts_out);
+
+size_t dawn_index_size(const dawn_index *idx);
+size_t dawn_index_capacity(const dawn_index *idx);
+size_t dawn_index_dimensions(const dawn_index *idx);
+
+/* Persist / restore the stored corpus (fp16 rows + labels) at `path`. */
+int dawn_index_save(dawn_index *idx, const char *path);
+int dawn_index_load(dawn_index *idx, const char *path);
+
+/* Stored vector for `label` decoded to f32 (SearchProvider::embedding_for_page,
+ * search_provider.rs:183-195, served from the device corpus).  DAWN_ERR_INVALID if absent. */
+int dawn_index_get(dawn_index *idx, uint64_t label, float *vector384_out);
+
+/* ---- device-resident entry points (no host<->device copies inside the call) -------------
+ * For callers that already hold queries / want results in device memory (a batching
+ * front-end, the multi-GPU merge, bench.py's kernel-only timing).  `stream` is a
+ * cudaStream_t passed as void* (NULL = the index's own stream); the call only enqueues.
+ * counts_out / flags_out are uint32 per query; flags bit0 = exactness certified. */
+int dawn_index_search_device(dawn_index *idx, const float *d_queries, size_t batch, size_t k,
+                             uint64_t *d_labels_out, float *d_distances_out,
+                             uint32_t *d_counts_out, uint32_t *d_flags_out, void *stream);
+/* Merge `n_lists` per-shard result lists (each [batch][k] labels + distances, ascending,
+ * with per-list counts) into one [batch][k] list; the device-side step after the
+ * all-gather of a sharded search (the role of search_remote's BestResults merge,
+ * src/search/search_service.rs:247-268). */
+int dawn_merge_results_device(int device, const uint64_t *d_labels, const float *d_distances,
+                              const uint32_t *d_counts, size_t n_lists, size_t batch, size_t k,
+                              uint64_t *d_labels_out, float *d_distances_out,
+                              uint32_t *d_counts_out, void *stream);
+/* Fill rows [size, size+n) with the synthetic corpus (seed, first_row..) generated on the
+ * device; labels are first_row + i + 1.  Test / bench aid: 100M vectors cannot cross PCIe in
+ * a test budget.  Bit-identical to oracle/dawn_oracle.c:dawn_oracle_synth_rows_f16. */
+int dawn_index_add_synthetic(dawn_index *idx, uint64_t seed, uint64_t first_row, size_t n);
+
+/* ---- instrumentation ------------------------------------------------------------------- */
+typedef struct dawn_profile {
+    uint64_t scan_launches;  /* K2 launches since the last reset */
+    double scan_ms;          /* summed CUDA-event time of those launches (on their stream) */
+    uint64_t finalize_launches;
+    double finalize_ms;
+    uint64_t queries;        /* queries answered */
+    uint64_t uncertified;    /* queries whose exactness certificate did not hold */
+    uint64_t escalations;    /* queries re-run with a longer candidate list */
+    uint64_t kernel_launches; /* all kernels launched by the library since the last reset */
+} dawn_profile;
+/* enable != 0: record CUDA events around every K2 / finalize launch (adds host syncs when
+ * read).  Off by default. */
+int dawn_index_set_profiling(dawn_index *idx, int enable);
+int dawn_index_get_profile(dawn_index *idx, dawn_profile *out, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
