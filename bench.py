@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", default="", help="extra device-resident points: 'batch[:k],...' e.g. 1,4,16:100")
     return ap.parse_args()
 
 
@@ -168,8 +169,8 @@ def run_ours(args):
     import torch.distributed as dist
 
     import dawnsearch_b200 as D
+    from dawnsearch_b200 import synth as O  # workload generator (numpy twin of the device generator)
     from dawnsearch_b200.sharded import ShardedIndex
-    from oracle import oracle as O  # query generation + the cpu_baseline leg only
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -255,6 +256,36 @@ def run_ours(args):
         assert int(probe[0][0][0]) == int(planted[0]) + 1, "planted neighbour not returned first"
         sh.index.profile(reset=True)
 
+    # ---- optional sweep over (batch, k): device-resident, 3 warm-up + 10 timed steps each ---
+    sweep = []
+    if args.sweep:
+        for item in args.sweep.split(","):
+            sb, sk = (int(x) for x in item.split(":")) if ":" in item else (int(item), k)
+            q = torch.from_numpy(O.make_queries(SEED, SEED + 5, sb, args.rows)).to(dev)
+            for _ in range(3):
+                sh.search_device(q, sk)
+            barrier()
+            sh.index.set_profiling(True)
+            sh.index.profile(reset=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                sh.search_device(q, sk)
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1) / 10
+            p = sh.index.profile(reset=True)
+            sh.index.set_profiling(False)
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            pass_ms = p["scan_ms"] / max(int(p["scan_launches"]), 1)
+            sweep.append({"batch": sb, "k": sk, "qps": sb / (ms / 1e3), "ms_per_step": ms,
+                          "scan_passes": int(p["scan_launches"]) // 10, "scan_ms_per_pass": pass_ms,
+                          "scan_gbps": n_local * ROW_BYTES / (pass_ms / 1e3) / 1e9 if pass_ms > 0 else None,
+                          "finalize_ms": p["finalize_ms"] / max(int(p["finalize_launches"]), 1)})
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         scan_launches = max(int(prof["scan_launches"]), 1)
@@ -285,6 +316,8 @@ def run_ours(args):
             "exactness": {"uncertified_queries": int(prof["uncertified"]) + int(prof_e2e["uncertified"]),
                           "escalations": int(prof_e2e["escalations"])},
         }
+        if sweep:
+            line["batch_sweep"] = sweep
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_arm(args, steps=3, warmup=1, rows_total=args.rows)
             line["cpu_baseline"] = {kk: r[kk] for kk in ("value", "unit", "cores", "kind", "sample")}

@@ -36,8 +36,8 @@ constexpr float kScanEps = 3.0e-5f;      // bound on |scan score - exact score| 
 
 // merge kernel for sharded searches, defined at the bottom of this file
 cudaError_t launch_merge_results(const uint64_t *labels, const float *dist, const uint32_t *counts,
-                                 int n_lists, int batch, int k, uint64_t *labels_out, float *dist_out,
-                                 uint32_t *counts_out, cudaStream_t s);
+                                 int n_lists, size_t list_stride_bytes, int batch, int k, uint64_t *labels_out,
+                                 float *dist_out, uint32_t *counts_out, cudaStream_t s);
 cudaError_t launch_find_label(const uint64_t *labels, size_t n, uint64_t label, uint32_t *row_out,
                               cudaStream_t s);
 
@@ -716,9 +716,9 @@ int dawn_index_get_profile(dawn_index *idx, dawn_profile *out, int reset) {
 }
 
 int dawn_merge_results_device(int device, const uint64_t *d_labels, const float *d_distances,
-                              const uint32_t *d_counts, size_t n_lists, size_t batch, size_t k,
-                              uint64_t *d_labels_out, float *d_distances_out, uint32_t *d_counts_out,
-                              void *stream) {
+                              const uint32_t *d_counts, size_t n_lists, size_t list_stride_bytes,
+                              size_t batch, size_t k, uint64_t *d_labels_out, float *d_distances_out,
+                              uint32_t *d_counts_out, void *stream) {
     if (!d_labels || !d_distances || !d_counts || !d_labels_out || !d_distances_out || !d_counts_out)
         return fail(DAWN_ERR_INVALID, "null device pointer");
     if (k == 0 || k > DAWN_MAX_K || n_lists == 0 || n_lists * k > 1024)
@@ -727,8 +727,8 @@ int dawn_merge_results_device(int device, const uint64_t *d_labels, const float 
     if (batch == 0) return DAWN_OK;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess)
-        e = launch_merge_results(d_labels, d_distances, d_counts, (int)n_lists, (int)batch, (int)k, d_labels_out,
-                                 d_distances_out, d_counts_out, (cudaStream_t)stream);
+        e = launch_merge_results(d_labels, d_distances, d_counts, (int)n_lists, list_stride_bytes, (int)batch, (int)k,
+                                 d_labels_out, d_distances_out, d_counts_out, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(DAWN_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(e));
     return DAWN_OK;
 }
@@ -744,19 +744,22 @@ namespace {
 // one thread per input entry; rank = position in own list + binary-searched counts in the others.
 __global__ void __launch_bounds__(1024) merge_results_kernel(
     const uint64_t *__restrict__ labels, const float *__restrict__ dist, const uint32_t *__restrict__ counts,
-    int n_lists, int batch, int k, uint64_t *__restrict__ labels_out, float *__restrict__ dist_out,
-    uint32_t *__restrict__ counts_out) {
+    int n_lists, size_t stride_l, size_t stride_d, size_t stride_c, int batch, int k,
+    uint64_t *__restrict__ labels_out, float *__restrict__ dist_out, uint32_t *__restrict__ counts_out) {
     __shared__ uint64_t s_lab[1024];
     __shared__ float s_dist[1024];
     __shared__ int s_cnt[64];
     const int qi = blockIdx.x;
     const int tid = threadIdx.x;
     const int total = n_lists * k;
-    if (tid < n_lists) s_cnt[tid] = min((int)counts[(size_t)tid * batch + qi], k);
+    // list l's arrays start l * stride bytes after the base pointers (dense arrays or one packed
+    // block per shard as it arrives from the all-gather)
+    if (tid < n_lists)
+        s_cnt[tid] = min((int)reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(counts) + tid * stride_c)[qi], k);
     if (tid < total) {
         const int l = tid / k, p = tid % k;
-        s_lab[tid] = labels[((size_t)l * batch + qi) * k + p];
-        s_dist[tid] = dist[((size_t)l * batch + qi) * k + p];
+        s_lab[tid] = reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(labels) + l * stride_l)[(size_t)qi * k + p];
+        s_dist[tid] = reinterpret_cast<const float *>(reinterpret_cast<const char *>(dist) + l * stride_d)[(size_t)qi * k + p];
     }
     __syncthreads();
     int all = 0;
@@ -797,11 +800,17 @@ __global__ void __launch_bounds__(256) find_label_kernel(const uint64_t *__restr
 }
 
 cudaError_t launch_merge_results(const uint64_t *labels, const float *dist, const uint32_t *counts, int n_lists,
-                                 int batch, int k, uint64_t *labels_out, float *dist_out, uint32_t *counts_out,
-                                 cudaStream_t s) {
+                                 size_t list_stride_bytes, int batch, int k, uint64_t *labels_out, float *dist_out,
+                                 uint32_t *counts_out, cudaStream_t s) {
     if (n_lists > 64) return cudaErrorInvalidValue;
-    merge_results_kernel<<<batch, 1024, 0, s>>>(labels, dist, counts, n_lists, batch, k, labels_out, dist_out,
-                                                counts_out);
+    size_t sl = list_stride_bytes, sd = list_stride_bytes, sc = list_stride_bytes;
+    if (list_stride_bytes == 0) {  // dense [n_lists][batch][k] arrays
+        sl = (size_t)batch * k * sizeof(uint64_t);
+        sd = (size_t)batch * k * sizeof(float);
+        sc = (size_t)batch * sizeof(uint32_t);
+    }
+    merge_results_kernel<<<batch, 1024, 0, s>>>(labels, dist, counts, n_lists, sl, sd, sc, batch, k, labels_out,
+                                                dist_out, counts_out);
     return cudaGetLastError();
 }
 

@@ -121,7 +121,7 @@ def load_library() -> C.CDLL:
     L.dawn_index_search_batch.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp]
     L.dawn_index_search_device.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _vp]
     L.dawn_merge_results_device.argtypes = [C.c_int, _vp, _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t,
-                                            _vp, _vp, _vp, _vp]
+                                            C.c_size_t, _vp, _vp, _vp, _vp]
     for name in ("dawn_index_size", "dawn_index_capacity", "dawn_index_dimensions"):
         getattr(L, name).argtypes = [_vp]
         getattr(L, name).restype = C.c_size_t
@@ -263,6 +263,7 @@ def new_index(options: IndexOptions | None = None) -> Index:
 
 def merge_results_device(device: int, d_labels: int, d_dist: int, d_counts: int, n_lists: int,
                          batch: int, k: int, d_labels_out: int, d_dist_out: int, d_counts_out: int,
-                         stream: int = 0) -> None:
-    _check(load_library().dawn_merge_results_device(device, d_labels, d_dist, d_counts, n_lists, batch, k,
-                                                    d_labels_out, d_dist_out, d_counts_out, stream))
+                         stream: int = 0, list_stride_bytes: int = 0) -> None:
+    _check(load_library().dawn_merge_results_device(device, d_labels, d_dist, d_counts, n_lists,
+                                                    list_stride_bytes, batch, k, d_labels_out, d_dist_out,
+                                                    d_counts_out, stream))

@@ -4,9 +4,10 @@ The reference already answers a query this way across WAN peers: scatter the que
 instance returns its local top-k, the caller merges by distance
 (/root/reference/src/net/udp_service.rs:314-330, src/search/search_service.rs:201-277).  On
 one NVSwitch box the same shape becomes: local exact top-k on every GPU (libdawn_b200) ->
-ONE all-gather of k (label, distance) pairs per query over NCCL/NVLink -> device-side merge
-(dawn_merge_results_device).  Because every shard returns bit-exact distances, the merged
-result is bit-identical to a single index holding the whole corpus.
+ONE all-gather of a packed block of k (label, distance) pairs per query over NCCL/NVLink ->
+device-side merge (dawn_merge_results_device).  Because every shard returns bit-exact
+distances and the order is defined on (distance, label), the merged result is bit-identical
+to a single index holding the whole corpus.
 
 torch is plumbing here (device buffers, streams, torch.distributed); all compute is in
 libdawn_b200.so.
@@ -18,6 +19,38 @@ import torch
 import torch.distributed as dist
 
 from .index import EM_LEN, Index, IndexOptions, merge_results_device, new_index
+
+
+def shard_range(rank: int, world: int, rows: int):
+    """Contiguous id-range shard of `rank`: (first_row, n_rows).  ceil(rows/world) per rank, the
+    last ranks may hold fewer (or zero) rows."""
+    per = (rows + world - 1) // world
+    first = min(rank * per, rows)
+    return first, max(0, min(per, rows - first))
+
+
+class ResultBlock:
+    """One shard's answer for a batch, packed so that it crosses NVLink as ONE message:
+    [batch*k u64 labels][batch*k f32 distances][batch u32 counts], padded to 16 bytes."""
+
+    def __init__(self, batch: int, k: int):
+        self.batch, self.k = batch, k
+        self.off_dist = batch * k * 8
+        self.off_counts = self.off_dist + batch * k * 4
+        self.nbytes = (self.off_counts + batch * 4 + 15) // 16 * 16
+
+    def views(self, buf: torch.Tensor):
+        """(labels int64 [B,k], distances f32 [B,k], counts int32 [B]) aliasing a uint8 buffer."""
+        b, k = self.batch, self.k
+        return (buf[: self.off_dist].view(torch.int64).view(b, k),
+                buf[self.off_dist: self.off_counts].view(torch.float32).view(b, k),
+                buf[self.off_counts: self.off_counts + b * 4].view(torch.int32))
+
+
+def all_gather_blocks(local: torch.Tensor, gathered: torch.Tensor, group=None):
+    """The one exchange step of a sharded search: [nbytes] uint8 per rank -> [world, nbytes] on
+    every rank.  Backend-agnostic (NCCL on the GPUs, gloo in the CPU tests)."""
+    dist.all_gather_into_tensor(gathered.view(-1), local, group=group)
 
 
 class ShardedIndex:
@@ -40,43 +73,40 @@ class ShardedIndex:
         ws = self._ws.get(key)
         if ws is None:
             d = self.tdev
+            blk = ResultBlock(batch, k)
             ws = {
+                "blk": blk,
                 "q": torch.empty((batch, EM_LEN), dtype=torch.float32, device=d),
-                "labels": torch.empty((batch, k), dtype=torch.int64, device=d),
-                "dist": torch.empty((batch, k), dtype=torch.float32, device=d),
-                "counts": torch.empty(batch, dtype=torch.int32, device=d),
+                "local": torch.zeros(blk.nbytes, dtype=torch.uint8, device=d),
                 "flags": torch.empty(batch, dtype=torch.int32, device=d),
-                "g_labels": torch.empty((self.world, batch, k), dtype=torch.int64, device=d),
-                "g_dist": torch.empty((self.world, batch, k), dtype=torch.float32, device=d),
-                "g_counts": torch.empty((self.world, batch), dtype=torch.int32, device=d),
-                "o_labels": torch.empty((batch, k), dtype=torch.int64, device=d),
-                "o_dist": torch.empty((batch, k), dtype=torch.float32, device=d),
-                "o_counts": torch.empty(batch, dtype=torch.int32, device=d),
+                "gathered": torch.zeros((self.world, blk.nbytes), dtype=torch.uint8, device=d),
+                "out": torch.zeros(blk.nbytes, dtype=torch.uint8, device=d),
                 "h_q": torch.empty((batch, EM_LEN), dtype=torch.float32).pin_memory(),
-                "h_labels": torch.empty((batch, k), dtype=torch.int64).pin_memory(),
-                "h_dist": torch.empty((batch, k), dtype=torch.float32).pin_memory(),
-                "h_counts": torch.empty(batch, dtype=torch.int32).pin_memory(),
+                "h_out": torch.empty(blk.nbytes, dtype=torch.uint8).pin_memory(),
             }
             self._ws[key] = ws
         return ws
 
     def search_device(self, d_queries: torch.Tensor, k: int):
-        """Queries already on this rank's GPU ([B,384] f32).  Enqueues local search, all-gather and
-        merge on the current stream; returns device tensors (labels int64, distances, counts)."""
+        """Queries already on this rank's GPU ([B,384] f32).  Enqueues local search, the all-gather
+        and the merge on the current stream; returns the packed result block (uint8, device) that
+        `ResultBlock.views` decodes."""
         batch = d_queries.shape[0]
         ws = self._workspace(batch, k)
-        stream = torch.cuda.current_stream(self.tdev).cuda_stream
-        self.index.search_device(d_queries.data_ptr(), batch, k, ws["labels"].data_ptr(), ws["dist"].data_ptr(),
-                                 ws["counts"].data_ptr(), ws["flags"].data_ptr(), stream)
+        blk: ResultBlock = ws["blk"]
+        # torch reports the legacy default stream as 0, which the C ABI reads as "the index's own
+        # stream"; cudaStreamLegacy (0x1) names the default stream explicitly.
+        stream = torch.cuda.current_stream(self.tdev).cuda_stream or 1
+        base = ws["local"].data_ptr()
+        self.index.search_device(d_queries.data_ptr(), batch, k, base, base + blk.off_dist, base + blk.off_counts,
+                                 ws["flags"].data_ptr(), stream)
         if self.world == 1:
-            return ws["labels"], ws["dist"], ws["counts"]
-        dist.all_gather_into_tensor(ws["g_labels"], ws["labels"], group=self.group)
-        dist.all_gather_into_tensor(ws["g_dist"], ws["dist"], group=self.group)
-        dist.all_gather_into_tensor(ws["g_counts"], ws["counts"], group=self.group)
-        merge_results_device(self.device, ws["g_labels"].data_ptr(), ws["g_dist"].data_ptr(),
-                             ws["g_counts"].data_ptr(), self.world, batch, k, ws["o_labels"].data_ptr(),
-                             ws["o_dist"].data_ptr(), ws["o_counts"].data_ptr(), stream)
-        return ws["o_labels"], ws["o_dist"], ws["o_counts"]
+            return ws["local"]
+        all_gather_blocks(ws["local"], ws["gathered"], self.group)
+        g, o = ws["gathered"].data_ptr(), ws["out"].data_ptr()
+        merge_results_device(self.device, g, g + blk.off_dist, g + blk.off_counts, self.world, batch, k,
+                             o, o + blk.off_dist, o + blk.off_counts, stream, list_stride_bytes=blk.nbytes)
+        return ws["out"]
 
     def search(self, queries: np.ndarray, k: int):
         """Host queries in, host results out (every rank gets the full merged answer)."""
@@ -86,10 +116,8 @@ class ShardedIndex:
         with torch.cuda.device(self.tdev):
             ws["h_q"].copy_(torch.from_numpy(q))
             ws["q"].copy_(ws["h_q"], non_blocking=True)
-            labels, dists, counts = self.search_device(ws["q"], k)
-            ws["h_labels"].copy_(labels, non_blocking=True)
-            ws["h_dist"].copy_(dists, non_blocking=True)
-            ws["h_counts"].copy_(counts, non_blocking=True)
+            out = self.search_device(ws["q"], k)
+            ws["h_out"].copy_(out, non_blocking=True)
             torch.cuda.current_stream(self.tdev).synchronize()
-        return (ws["h_labels"].numpy().astype(np.uint64), ws["h_dist"].numpy().copy(),
-                ws["h_counts"].numpy().astype(np.int64))
+        labels, dists, counts = ws["blk"].views(ws["h_out"])
+        return (labels.numpy().astype(np.uint64), dists.numpy().copy(), counts.numpy().astype(np.int64))

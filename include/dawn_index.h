@@ -119,12 +119,15 @@ int dawn_index_search_device(dawn_index *idx, const float *d_queries, size_t bat
                              uint64_t *d_labels_out, float *d_distances_out,
                              uint32_t *d_counts_out, uint32_t *d_flags_out, void *stream);
 /* Merge `n_lists` per-shard result lists (each [batch][k] labels + distances, ascending,
- * with per-list counts) into one [batch][k] list; the device-side step after the
- * all-gather of a sharded search (the role of search_remote's BestResults merge,
- * src/search/search_service.rs:247-268). */
+ * with [batch] counts) into one [batch][k] list; the device-side step after the all-gather of
+ * a sharded search (the role of search_remote's BestResults merge,
+ * src/search/search_service.rs:247-268).  List l's three arrays start l*list_stride_bytes
+ * after the three base pointers, so one packed block per shard (as it lands from a single
+ * all-gather) can be merged in place; list_stride_bytes == 0 means three dense arrays
+ * [n_lists][batch][k] / [n_lists][batch].  n_lists*k <= 1024. */
 int dawn_merge_results_device(int device, const uint64_t *d_labels, const float *d_distances,
-                              const uint32_t *d_counts, size_t n_lists, size_t batch, size_t k,
-                              uint64_t *d_labels_out, float *d_distances_out,
+                              const uint32_t *d_counts, size_t n_lists, size_t list_stride_bytes,
+                              size_t batch, size_t k, uint64_t *d_labels_out, float *d_distances_out,
                               uint32_t *d_counts_out, void *stream);
 /* Fill rows [size, size+n) with the synthetic corpus (seed, first_row..) generated on the
  * device; labels are first_row + i + 1.  Test / bench aid: 100M vectors cannot cross PCIe in
