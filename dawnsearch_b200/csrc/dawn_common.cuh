@@ -117,9 +117,30 @@ struct FinalizeLaunch {
     float *distances_out;   // [nq][k]
     uint32_t *counts_out;   // [nq]
     uint32_t *flags_out;    // [nq] bit0 = exactness certified
+    const float *eps_q;     // optional per-query eps (GEMM path: depends on the query's fp16 rounding)
+    const uint32_t *overflow;  // optional per-query "candidate log overflowed" flags -> not certified
 };
 // K5+K6: merge per-CTA lists, re-score candidates in the reference's order of summation
 // (src/search/vector.rs:128-134), final order and 1 - score.
 cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s);
+
+struct GemmSearch {
+    const __half *corpus;     // [n_rows][384] fp16
+    const uint64_t *labels;   // [n_rows]
+    uint64_t n_rows;
+    const float *queries;     // [n_queries][384] f32, device
+    int n_queries;
+    int kprime;               // candidates kept per query (<= 128)
+    int grid;                 // CTAs (= SM count)
+    void *workspace;          // gemm_workspace_bytes(n_queries)
+    Cand *final_lists;        // out: [ceil128(n_queries)][kprime] sorted candidates (approximate scores)
+    float accum_slack;        // bound on the tensor-core accumulation error added to every eps_q
+    const float **eps_out;    // out: device pointer to per-query eps
+    const uint32_t **overflow_out;  // out: device pointer to per-query overflow flags
+    int *launches_out;        // out: kernels launched
+};
+// K3: tcgen05 GEMM + fused top-k' over geometrically growing rounds of rows (gemm_topk.cu).
+cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s);
+size_t gemm_workspace_bytes(int n_queries);
 
 }  // namespace dawn

@@ -43,8 +43,9 @@ cudaError_t launch_find_label(const uint64_t *labels, size_t n, uint64_t label, 
 
 struct EventPair {
     cudaEvent_t a, b;
-    int kind;  // 0 scan, 1 finalize
+    int kind;  // 0 scan, 1 finalize, 2 gemm (all rounds of one batch)
 };
+constexpr float kGemmAccumSlack = 6.0e-5f;  // tensor-core f32 accumulation over K=384
 
 }  // namespace
 
@@ -80,6 +81,12 @@ struct dawn_index {
     uint32_t *d_counters = nullptr;  // one chunk counter per scan pass, + status word at [0]
     size_t counters_cap = 0;
     uint32_t *h_word = nullptr;  // pinned scratch word
+    void *d_gemm_ws = nullptr;   // K3 workspace (fp16 queries, eps, thresholds, candidate logs)
+    size_t gemm_ws_cap = 0;
+    // path selection: batches >= gemm_min_batch over >= gemm_min_rows rows take the tensor-core path
+    int64_t gemm_min_batch = 16;
+    int64_t gemm_min_rows = 65536;
+    int64_t force_path = 0;  // 0 auto, 1 scan only, 2 gemm whenever possible
 
     bool profiling = false;
     std::vector<EventPair> pending;
@@ -117,7 +124,8 @@ void drain_events(dawn_index *idx) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
             if (p.kind == 0) idx->prof.scan_ms += ms;
-            else idx->prof.finalize_ms += ms;
+            else if (p.kind == 1) idx->prof.finalize_ms += ms;
+            else idx->prof.gemm_ms += ms;
         }
         idx->free_events.push_back(p);
     }
@@ -242,8 +250,80 @@ int ensure_query_ws(dawn_index *idx, size_t batch, size_t k) {
 // Enqueue the whole search for `batch` device-resident queries on stream `s`.
 int search_enqueue(dawn_index *idx, const float *d_queries, size_t batch, size_t k, int kprime,
                    uint64_t *d_labels_out, float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags,
-                   cudaStream_t s) {
+                   cudaStream_t s, bool scan_only = false) {
     const int grid = idx->sm_count;
+    const bool gemm_ok = idx->size >= 1024 && batch >= 1;
+    const bool use_gemm = gemm_ok && !scan_only && idx->force_path != 1 &&
+                          (idx->force_path == 2 ||
+                           ((int64_t)batch >= idx->gemm_min_batch && (int64_t)idx->size >= idx->gemm_min_rows));
+    if (use_gemm) {
+        const size_t qp = (batch + 127) / 128 * 128;
+        const size_t need_ws = gemm_workspace_bytes((int)batch);
+        if (need_ws > idx->gemm_ws_cap) {
+            if (idx->d_gemm_ws) cudaFree(idx->d_gemm_ws);
+            idx->gemm_ws_cap = 0;
+            CK(idx, cudaMalloc(&idx->d_gemm_ws, need_ws));
+            idx->gemm_ws_cap = need_ws;
+        }
+        if (qp * kprime > idx->partials_cap) {
+            if (idx->d_partials) cudaFree(idx->d_partials);
+            idx->partials_cap = 0;
+            CK(idx, cudaMalloc(&idx->d_partials, qp * kprime * sizeof(Cand)));
+            idx->partials_cap = qp * kprime;
+        }
+        if (idx->counters_cap < 1) {
+            CK(idx, cudaMalloc(&idx->d_counters, 1024 * sizeof(uint32_t)));
+            idx->counters_cap = 1024;
+        }
+        CK(idx, cudaMemsetAsync(idx->d_counters, 0, sizeof(uint32_t), s));
+        GemmSearch gs;
+        gs.corpus = idx->corpus;
+        gs.labels = idx->labels;
+        gs.n_rows = idx->size;
+        gs.queries = d_queries;
+        gs.n_queries = (int)batch;
+        gs.kprime = kprime;
+        gs.grid = grid;
+        gs.workspace = idx->d_gemm_ws;
+        gs.final_lists = idx->d_partials;
+        gs.accum_slack = kGemmAccumSlack;
+        const float *eps_q = nullptr;
+        const uint32_t *overflow = nullptr;
+        int launches = 0;
+        gs.eps_out = &eps_q;
+        gs.overflow_out = &overflow;
+        gs.launches_out = &launches;
+        EventPair evg;
+        bool timedg = begin_event(idx, 2, s, &evg);
+        CK(idx, launch_gemm_search(gs, s));
+        if (timedg) end_event(idx, evg, s);
+        idx->prof.gemm_batches++;
+        idx->prof.kernel_launches += launches;
+        FinalizeLaunch fl;
+        fl.corpus = idx->corpus;
+        fl.queries = d_queries;
+        fl.nq = (int)batch;
+        fl.partials = idx->d_partials;
+        fl.n_lists = 1;
+        fl.kprime = kprime;
+        fl.k = (int)k;
+        fl.eps = 0.f;
+        fl.labels_out = d_labels_out;
+        fl.distances_out = d_dist_out;
+        fl.counts_out = d_counts;
+        fl.flags_out = d_flags;
+        fl.eps_q = eps_q;
+        fl.overflow = overflow;
+        EventPair evf;
+        bool timedf = begin_event(idx, 1, s, &evf);
+        CK(idx, launch_finalize(fl, s));
+        if (timedf) end_event(idx, evf, s);
+        idx->prof.finalize_launches++;
+        idx->prof.kernel_launches++;
+        idx->prof.queries += batch;
+        if (idx->pending.size() > 4096) drain_events(idx);
+        return DAWN_OK;
+    }
     const size_t need_partials = batch * (size_t)grid * kprime;
     if (need_partials > idx->partials_cap) {
         if (idx->d_partials) cudaFree(idx->d_partials);
@@ -300,6 +380,8 @@ int search_enqueue(dawn_index *idx, const float *d_queries, size_t batch, size_t
     fl.distances_out = d_dist_out;
     fl.counts_out = d_counts;
     fl.flags_out = d_flags;
+    fl.eps_q = nullptr;
+    fl.overflow = nullptr;
     EventPair ev;
     bool timed = begin_event(idx, 1, s, &ev);
     CK(idx, launch_finalize(fl, s));
@@ -402,6 +484,7 @@ void dawn_index_free(dawn_index *idx) {
     cudaFreeHost(idx->h_flags);
     cudaFree(idx->d_partials);
     cudaFree(idx->d_counters);
+    cudaFree(idx->d_gemm_ws);
     cudaFreeHost(idx->h_word);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     cudaGetLastError();
@@ -495,6 +578,7 @@ int dawn_index_search_batch(dawn_index *idx, const float *queries, size_t batch,
     memcpy(idx->h_queries, queries, batch * kDim * sizeof(float));
     CK(idx, cudaMemcpyAsync(idx->d_queries, idx->h_queries, batch * kDim * sizeof(float), cudaMemcpyHostToDevice, s));
     int kprime = choose_kprime(k);
+    const uint64_t gemm_before = idx->prof.gemm_batches;
     rc = search_enqueue(idx, idx->d_queries, batch, k, kprime, idx->d_labels_out, idx->d_dist_out, idx->d_counts,
                         idx->d_flags, s);
     if (rc) return rc;
@@ -511,12 +595,13 @@ int dawn_index_search_batch(dawn_index *idx, const float *queries, size_t batch,
 
     // Exactness certificate not met (near-ties deeper than the slack): re-run those queries
     // with the longest candidate list.
-    if (kprime < kMaxCand) {
+    const bool can_escalate = kprime < kMaxCand || idx->prof.gemm_batches > gemm_before;
+    if (can_escalate) {
         for (size_t b = 0; b < batch; b++) {
             if (idx->h_flags[b] & 1u) continue;
             idx->prof.escalations++;
             rc = search_enqueue(idx, idx->d_queries + b * kDim, 1, k, kMaxCand, idx->d_labels_out, idx->d_dist_out,
-                                idx->d_counts, idx->d_flags, s);
+                                idx->d_counts, idx->d_flags, s, /*scan_only=*/true);
             if (rc) return rc;
             CK(idx, cudaMemcpyAsync(idx->h_labels_out, idx->d_labels_out, k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
             CK(idx, cudaMemcpyAsync(idx->h_dist_out, idx->d_dist_out, k * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -692,6 +777,18 @@ int dawn_index_load(dawn_index *idx, const char *path) {
     if (!ok) return fail(DAWN_ERR_IO, "read error on %s", path);
     idx->size = h.size;
     if (idx->capacity < idx->size) idx->capacity = idx->size;
+    return DAWN_OK;
+}
+
+int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value) {
+    int rc = check_alive(idx);
+    if (rc) return rc;
+    if (!key) return fail(DAWN_ERR_INVALID, "key is null");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if (!strcmp(key, "gemm_min_batch")) idx->gemm_min_batch = value;
+    else if (!strcmp(key, "gemm_min_rows")) idx->gemm_min_rows = value;
+    else if (!strcmp(key, "force_path")) idx->force_path = value;
+    else return fail(DAWN_ERR_INVALID, "unknown option '%s'", key);
     return DAWN_OK;
 }
 

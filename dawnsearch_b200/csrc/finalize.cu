@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(kFinThreads, 1)
 finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ queries,
                 const Cand *__restrict__ partials, int n_lists, int kp, int k, float eps,
                 uint64_t *__restrict__ labels_out, float *__restrict__ distances_out,
-                uint32_t *__restrict__ counts_out, uint32_t *__restrict__ flags_out) {
+                uint32_t *__restrict__ counts_out, uint32_t *__restrict__ flags_out,
+                const float *__restrict__ eps_q, const uint32_t *__restrict__ overflow) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FinSmem &sm = *reinterpret_cast<FinSmem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -163,9 +164,11 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
             // A row outside the candidate set has scan score <= scan_min, hence exact score
             // <= scan_min + eps and distance >= 1 - (scan_min + eps); it cannot displace or tie
             // the k-th result if that bound is strictly above the k-th distance.
-            const float bound = __fsub_rn(1.0f, __fadd_rn(sm.scan_score[kp - 1], eps));
+            const float e = eps_q ? eps_q[qi] : eps;
+            const float bound = __fsub_rn(1.0f, __fadd_rn(sm.scan_score[kp - 1], e));
             certified = bound > sm.kth_dist;
         }
+        if (overflow && overflow[qi]) certified = false;  // candidates were lost: cannot certify
         flags_out[qi] = certified ? 1u : 0u;
     }
 }
@@ -185,7 +188,7 @@ cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s) {
     }
     finalize_kernel<<<p.nq, kFinThreads, smem, s>>>(p.corpus, p.queries, p.partials, p.n_lists,
                                                    p.kprime, p.k, p.eps, p.labels_out, p.distances_out,
-                                                   p.counts_out, p.flags_out);
+                                                   p.counts_out, p.flags_out, p.eps_q, p.overflow);
     return cudaGetLastError();
 }
 

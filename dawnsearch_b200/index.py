@@ -68,6 +68,8 @@ class Profile(C.Structure):
         ("uncertified", C.c_uint64),
         ("escalations", C.c_uint64),
         ("kernel_launches", C.c_uint64),
+        ("gemm_batches", C.c_uint64),
+        ("gemm_ms", C.c_double),
     ]
 
     def as_dict(self):
@@ -130,6 +132,7 @@ def load_library() -> C.CDLL:
     L.dawn_index_get.argtypes = [_vp, C.c_uint64, _vp]
     L.dawn_index_add_synthetic.argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_size_t]
     L.dawn_index_set_profiling.argtypes = [_vp, C.c_int]
+    L.dawn_index_set_option.argtypes = [_vp, C.c_char_p, C.c_int64]
     L.dawn_index_get_profile.argtypes = [_vp, C.POINTER(Profile), C.c_int]
     _lib = L
     return L
@@ -246,6 +249,10 @@ class Index:
         """Raw device-pointer entry point (ints are CUDA device addresses); only enqueues."""
         _check(self._L.dawn_index_search_device(self._h, d_queries, batch, count, d_labels, d_dist,
                                                 d_counts, d_flags, stream))
+
+    def set_option(self, key: str, value: int) -> None:
+        """'gemm_min_batch', 'gemm_min_rows', 'force_path' (0 auto, 1 scan, 2 tensor-core)."""
+        _check(self._L.dawn_index_set_option(self._h, key.encode(), int(value)))
 
     def set_profiling(self, enable: bool) -> None:
         _check(self._L.dawn_index_set_profiling(self._h, int(enable)))

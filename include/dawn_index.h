@@ -144,10 +144,16 @@ typedef struct dawn_profile {
     uint64_t uncertified;    /* queries whose exactness certificate did not hold */
     uint64_t escalations;    /* queries re-run with a longer candidate list */
     uint64_t kernel_launches; /* all kernels launched by the library since the last reset */
+    uint64_t gemm_batches;   /* batches answered by the tensor-core path (K3) */
+    double gemm_ms;          /* summed CUDA-event time of those batches (all rounds, excl. finalize) */
 } dawn_profile;
 /* enable != 0: record CUDA events around every K2 / finalize launch (adds host syncs when
  * read).  Off by default. */
 int dawn_index_set_profiling(dawn_index *idx, int enable);
+/* Tuning knobs: "gemm_min_batch" (default 16) and "gemm_min_rows" (default 65536) decide when a
+ * batch takes the tensor-core path instead of repeated streaming scans; "force_path" 0 = auto,
+ * 1 = scan only, 2 = tensor-core path whenever the corpus holds >= 1024 vectors. */
+int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value);
 int dawn_index_get_profile(dawn_index *idx, dawn_profile *out, int reset);
 
 #ifdef __cplusplus

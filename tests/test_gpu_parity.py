@@ -272,3 +272,88 @@ def test_full_size_properties_10m(dawn, oracle):
     assert (Co.cpu().numpy() == 10).all()
     assert (Lo.cpu().numpy().astype(np.uint64) == whole[0]).all()
     assert (bits(Do.cpu().numpy()) == bits(whole[1])).all()
+
+
+# ------------------------------------------------------------------ K3: tensor-core path
+
+
+@pytest.fixture(scope="module")
+def index300k(dawn):
+    n = 300_000
+    idx = dawn.new_index(dawn.IndexOptions(capacity=n))
+    idx.add_synthetic(SEED, 0, n)
+    yield idx, n
+    idx.close()
+
+
+@pytest.fixture(scope="module")
+def stored300k(oracle):
+    return oracle.synth_rows_f16(SEED, 0, 300_000)
+
+
+@pytest.mark.parametrize("batch,k", [(1, 10), (7, 20), (16, 10), (128, 10), (129, 100), (300, 100), (1024, 10)])
+def test_gemm_path_matches_oracle(index300k, stored300k, oracle, batch, k):
+    """Large batches run as tcgen05 tiles with the top-k fused in the epilogue; the fp16-rounded
+    queries only SELECT candidates, so labels and distances are still bit-identical."""
+    idx, n = index300k
+    idx.set_option("force_path", 2)
+    try:
+        idx.profile(reset=True)
+        qs = oracle.make_queries(SEED, 1000 + batch, batch, n)
+        gl, gd, cnt = idx.search_batch(qs, k)
+        prof = idx.profile(reset=True)
+        assert prof["gemm_batches"] == 1 and prof["scan_launches"] == 0  # really the tensor-core path
+        assert prof["escalations"] == 0 and prof["uncertified"] == 0
+        wl, wd, wc, _ = oracle.cpu_scan_f16(stored300k, None, qs, k)
+        assert (cnt == wc).all()
+        assert (gl == wl).all()
+        assert (bits(gd) == bits(wd)).all()
+    finally:
+        idx.set_option("force_path", 0)
+
+
+@pytest.mark.parametrize("n", [1024, 1025, 1279, 1280, 4097, 70_001])
+def test_gemm_path_ragged_row_counts(dawn, oracle, n):
+    rows = oracle.np_synth_rows_f32(4242, 0, n)
+    stored = oracle.store_f16(rows)
+    labels = perm_labels(oracle, n, salt=11, base=7)
+    with dawn.new_index(dawn.IndexOptions()) as idx:
+        idx.reserve(n)
+        idx.add_batch(labels, rows)
+        idx.set_option("force_path", 2)
+        qs = oracle.make_queries(4242, 4243, 20, n)
+        for k in (10, 100):
+            gl, gd, cnt = idx.search_batch(qs, k)
+            for i, q in enumerate(qs):
+                assert_same((gl[i, : cnt[i]], gd[i, : cnt[i]]), oracle.search_f16(stored, labels, q, k), f"n={n} k={k} i={i}")
+        assert idx.profile()["gemm_batches"] == 2
+
+
+def test_gemm_path_duplicates_escalate_to_exact_scan(dawn, oracle):
+    """Thousands of identical pages: the tensor-core path cannot certify the label tie-break,
+    the host API re-runs those queries through the exact scan, results stay exact."""
+    base = oracle.np_synth_rows_f32(5, 0, 2)
+    rows = np.concatenate([np.repeat(base[:1], 3000, axis=0), oracle.np_synth_rows_f32(6, 0, 2000)])
+    n = len(rows)
+    labels = perm_labels(oracle, n, salt=13)
+    stored = oracle.store_f16(rows)
+    with dawn.new_index(dawn.IndexOptions()) as idx:
+        idx.reserve(n)
+        idx.add_batch(labels, rows)
+        idx.set_option("force_path", 2)
+        qs = np.stack([base[0], base[1]])
+        gl, gd, cnt = idx.search_batch(qs, 10)
+        for i, q in enumerate(qs):
+            assert_same((gl[i], gd[i]), oracle.search_f16(stored, labels, q, 10), f"i={i}")
+        assert idx.profile()["escalations"] >= 1
+
+
+def test_auto_path_selection(index300k, oracle):
+    idx, n = index300k
+    idx.profile(reset=True)
+    idx.search_batch(oracle.make_queries(SEED, 1, 4, n), 10)
+    p = idx.profile(reset=True)
+    assert p["gemm_batches"] == 0 and p["scan_launches"] == 1
+    idx.search_batch(oracle.make_queries(SEED, 2, 64, n), 10)
+    p = idx.profile(reset=True)
+    assert p["gemm_batches"] == 1 and p["scan_launches"] == 0
