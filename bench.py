@@ -171,7 +171,7 @@ def run_reference(args):
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print_json(line)
 
 
 def run_ours(args):
@@ -354,7 +354,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_arm(args, steps=2, warmup=1, rows_total=args.rows)
             line["cpu_baseline"] = {kk: r[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        print_json(line)
     sh.close()
     if world > 1:
         dist.barrier()
@@ -363,10 +363,26 @@ def run_ours(args):
 
 def main():
     args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # Only the JSON line may reach stdout (NCCL and torchrun print banners there): park the real
+    # stdout, point fd 1 at stderr while working, and restore it for the final print.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    line_holder = []
+    global print_json
+    def print_json(obj):
+        line_holder.append(json.dumps(obj))
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in line_holder:
+        print(ln, flush=True)
 
 
 if __name__ == "__main__":

@@ -86,6 +86,8 @@ struct dawn_index {
     // path selection: batches >= gemm_min_batch over >= gemm_min_rows rows take the tensor-core path
     int64_t gemm_min_batch = 16;
     int64_t gemm_min_rows = 65536;
+    int64_t gemm_small_batch = 3;          // from this batch size on, big corpora also take the tensor path
+    int64_t gemm_small_batch_rows = 2000000;
     int64_t force_path = 0;  // 0 auto, 1 scan only, 2 gemm whenever possible
 
     bool profiling = false;
@@ -255,7 +257,8 @@ int search_enqueue(dawn_index *idx, const float *d_queries, size_t batch, size_t
     const bool gemm_ok = idx->size >= 1024 && batch >= 1;
     const bool use_gemm = gemm_ok && !scan_only && idx->force_path != 1 &&
                           (idx->force_path == 2 ||
-                           ((int64_t)batch >= idx->gemm_min_batch && (int64_t)idx->size >= idx->gemm_min_rows));
+                           ((int64_t)batch >= idx->gemm_min_batch && (int64_t)idx->size >= idx->gemm_min_rows) ||
+                           ((int64_t)batch >= idx->gemm_small_batch && (int64_t)idx->size >= idx->gemm_small_batch_rows));
     if (use_gemm) {
         const size_t qp = (batch + 127) / 128 * 128;
         const size_t need_ws = gemm_workspace_bytes((int)batch);
@@ -787,6 +790,8 @@ int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value) {
     std::lock_guard<std::mutex> lk(idx->mu);
     if (!strcmp(key, "gemm_min_batch")) idx->gemm_min_batch = value;
     else if (!strcmp(key, "gemm_min_rows")) idx->gemm_min_rows = value;
+    else if (!strcmp(key, "gemm_small_batch")) idx->gemm_small_batch = value;
+    else if (!strcmp(key, "gemm_small_batch_rows")) idx->gemm_small_batch_rows = value;
     else if (!strcmp(key, "force_path")) idx->force_path = value;
     else return fail(DAWN_ERR_INVALID, "unknown option '%s'", key);
     return DAWN_OK;

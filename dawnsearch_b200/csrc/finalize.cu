@@ -20,17 +20,19 @@ namespace dawn {
 
 namespace {
 
-constexpr int kFinThreads = 1024;
+constexpr int kFinThreads = 1024;     // merging 148 per-CTA lists (scan path)
+constexpr int kFinThreadsSingle = 128;  // one pre-merged list per query (tensor-core path)
 constexpr int kFinCapEntries = 4096;  // 64 KB of candidates in shared memory per round
 constexpr int kFinItems = kFinCapEntries / kFinThreads;
 
 struct FinSmem {
-    alignas(16) Cand s[kFinCapEntries];
     alignas(16) float q[kDim];
     float scan_score[kMaxCand];
     uint32_t n_valid;
     float kth_dist;
+    alignas(16) Cand s[1];  // kFinCapEntries entries when merging, kp entries for a single list
 };
+inline size_t fin_smem_bytes(int entries) { return sizeof(FinSmem) + (size_t)(entries - 1) * sizeof(Cand); }
 
 __device__ __forceinline__ bool dist_before(const Cand &a, const Cand &b) {
     if (a.score != b.score) return a.score < b.score;
@@ -89,21 +91,26 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
     const int qi = blockIdx.x;
     const Cand *lists = partials + (size_t)qi * n_lists * kp;
 
-    for (int c = tid; c < kDim; c += kFinThreads) sm.q[c] = queries[(size_t)qi * kDim + c];
+    const int nthr = blockDim.x;
+    for (int c = tid; c < kDim; c += nthr) sm.q[c] = queries[(size_t)qi * kDim + c];
 
     // ---- K5: streaming tree merge, cap_lists lists per round, list 0 is the running result
-    const int cap_lists = kFinCapEntries / kp;
-    int next = 0;
-    bool first = true;
-    while (next < n_lists || first) {
-        const int keep = first ? 0 : 1;
-        const int take = min(cap_lists - keep, n_lists - next);
-        for (int i = tid; i < take * kp; i += kFinThreads)
-            sm.s[keep * kp + i] = lists[(size_t)next * kp + i];
-        __syncthreads();
-        merge_lists(sm.s, keep + take, kp, tid);
-        next += take;
-        first = false;
+    if (n_lists == 1) {  // already one sorted list (tensor-core path): nothing to merge
+        for (int i = tid; i < kp; i += nthr) sm.s[i] = lists[i];
+    } else {             // requires blockDim.x == kFinThreads
+        const int cap_lists = kFinCapEntries / kp;
+        int next = 0;
+        bool first = true;
+        while (next < n_lists || first) {
+            const int keep = first ? 0 : 1;
+            const int take = min(cap_lists - keep, n_lists - next);
+            for (int i = tid; i < take * kp; i += kFinThreads)
+                sm.s[keep * kp + i] = lists[(size_t)next * kp + i];
+            __syncthreads();
+            merge_lists(sm.s, keep + take, kp, tid);
+            next += take;
+            first = false;
+        }
     }
     __syncthreads();
 
@@ -179,14 +186,14 @@ cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s) {
     if (p.nq == 0) return cudaSuccess;
     if (p.kprime < 1 || p.kprime > kMaxCand || p.k < 1 || p.k > p.kprime) return cudaErrorInvalidValue;
     static bool configured = false;
-    const size_t smem = sizeof(FinSmem);
+    const size_t smem = fin_smem_bytes(p.n_lists == 1 ? p.kprime : kFinCapEntries);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+                                             (int)fin_smem_bytes(kFinCapEntries));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    finalize_kernel<<<p.nq, kFinThreads, smem, s>>>(p.corpus, p.queries, p.partials, p.n_lists,
+    finalize_kernel<<<p.nq, p.n_lists == 1 ? kFinThreadsSingle : kFinThreads, smem, s>>>(p.corpus, p.queries, p.partials, p.n_lists,
                                                    p.kprime, p.k, p.eps, p.labels_out, p.distances_out,
                                                    p.counts_out, p.flags_out, p.eps_q, p.overflow);
     return cudaGetLastError();

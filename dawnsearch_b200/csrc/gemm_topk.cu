@@ -130,13 +130,6 @@ struct GemmSmem {  // offsets from the 1024-aligned base
     // barriers (8 B each): full[3], empty[3], tmem_full[2], tmem_empty[2], a_full, a_free ; then tmem ptr
 };
 
-__device__ __noinline__ void append_candidate(uint2 *__restrict__ log_q, uint32_t *__restrict__ cnt_q,
-                                              uint32_t *__restrict__ overflow_q, float score, uint32_t row, int cap) {
-    const uint32_t slot = atomicAdd(cnt_q, 1u);
-    if (slot < (uint32_t)cap) log_q[slot] = make_uint2(__float_as_uint(score), row);
-    else *overflow_q = 1u;
-}
-
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                  uint32_t row_begin, uint32_t row_end, uint32_t n_rows, int n_qtiles, int n_queries,
@@ -284,12 +277,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
                     for (int i = 1; i < 32; i++) m = fmaxf(m, __uint_as_float(v[i]));
                     if (q_valid && m >= thr) {
+                        // Survivors of this 32-column chunk: ONE atomic reserves their slots (a
+                        // single round trip for the whole warp), then the stores are fire-and-forget.
+                        const int lim = (int)min(row_end, n_rows) - (int)(row0 + c * 32);
+                        uint32_t mask = 0;
 #pragma unroll
-                        for (int i = 0; i < 32; i++) {
-                            const float sc = __uint_as_float(v[i]);
-                            const uint32_t row = row0 + c * 32 + i;
-                            if (sc >= thr && row < row_end && row < n_rows)
-                                append_candidate(log_q, cnt_g + q, overflow_g + q, sc, row, log_cap);
+                        for (int i = 0; i < 32; i++) mask |= (__uint_as_float(v[i]) >= thr) ? (1u << i) : 0u;
+                        if (lim < 32) mask &= lim <= 0 ? 0u : ((1u << lim) - 1u);
+                        if (mask) {
+                            uint32_t slot = atomicAdd(cnt_g + q, (uint32_t)__popc(mask));
+#pragma unroll
+                            for (int i = 0; i < 32; i++) {
+                                if (mask & (1u << i)) {
+                                    if (slot < (uint32_t)log_cap) log_q[slot] = make_uint2(v[i], row0 + c * 32 + i);
+                                    else overflow_g[q] = 1u;
+                                    slot++;
+                                }
+                            }
                         }
                     }
                     __syncwarp();
@@ -338,7 +342,7 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float *__restri
 }
 
 // ---- select: keep the best k' log entries of a query, publish the k'-th score as threshold ----
-constexpr int kSelThreads = 1024;
+constexpr int kSelThreads = 256;  // enough for ~512 live entries per query; many CTAs per SM
 constexpr int kSelCap = 2048;  // == log capacity per query
 
 __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(uint2 *__restrict__ log_g, uint32_t *__restrict__ cnt_g,
