@@ -313,6 +313,42 @@ class BestResults:
         return out
 
 
+class Hnsw:
+    """HNSW restatement (NOT USearch 0.22.3; see hnsw_restatement.c): the reference's kind of
+    index with USearch's defaults (M=16, efConstruction=128, efSearch=64, IP on f32)."""
+
+    def __init__(self, M: int = 16, ef_construction: int = 128, ef_search: int = 64, seed: int = 1):
+        self._h = lib().dawn_hnsw_new(M, ef_construction, ef_search, seed)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().dawn_hnsw_free(self._h)
+            self._h = None
+
+    def add(self, label: int, vector) -> None:
+        v = _f32(vector)
+        lib().dawn_hnsw_add(self._h, int(label), _p(v))
+
+    def add_batch(self, labels, vectors) -> None:
+        vectors = _f32(vectors).reshape(-1, EM_LEN)
+        L = lib()
+        for lab, v in zip(labels, vectors):
+            L.dawn_hnsw_add(self._h, int(lab), C.c_void_p(v.ctypes.data))
+
+    def search(self, query, k: int):
+        q = _f32(query)
+        lo = np.zeros(max(k, 1), dtype=np.uint64)
+        do = np.zeros(max(k, 1), dtype=np.float32)
+        n = lib().dawn_hnsw_search(self._h, _p(q), k, _p(lo), _p(do))
+        return lo[:n].copy(), do[:n].copy()
+
+    def size(self) -> int:
+        return int(lib().dawn_hnsw_size(self._h))
+
+    def set_ef_search(self, ef: int) -> None:
+        lib().dawn_hnsw_set_ef_search(self._h, ef)
+
+
 # ------------------------------------------------------- numpy restatement
 
 

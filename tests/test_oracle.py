@@ -233,3 +233,27 @@ def test_cpu_scan_duplicates_fall_back_exactly(oracle):
     labels = np.arange(3000, 0, -1).astype(np.uint64)
     lo, do, cnt, cert = oracle.cpu_scan_f16(stored, labels, row.astype(np.float32), 10, threads=4)
     assert list(lo[0]) == list(range(1, 11))
+
+
+def test_hnsw_restatement_behaves_like_an_ann_index(oracle):
+    """The stand-in for the reference's USearch index (hnsw_restatement.c, NOT USearch 0.22.3):
+    approximate, ascending distances = 1 - dot, recall rising to 1 with efSearch."""
+    n = 3000
+    rows = oracle.np_synth_rows_f32(3, 0, n)
+    h = oracle.Hnsw(16, 128, 64, 1)
+    h.add_batch(np.arange(1, n + 1), rows)
+    assert h.size() == n
+    qs = oracle.make_queries(3, 4, 40, n)
+    truth = [oracle.search_f32(rows, None, q, 10) for q in qs]
+    recalls = []
+    for ef in (16, 64, 2000):
+        h.set_ef_search(ef)
+        hit = 0
+        for q, (tl, td) in zip(qs, truth):
+            l, d = h.search(q, 10)
+            assert len(l) == 10 and (np.diff(d) >= 0).all()
+            hit += len(set(l.tolist()) & set(tl.tolist()))
+        recalls.append(hit / 400)
+    assert recalls[0] <= recalls[1] <= recalls[2] and recalls[2] > 0.99
+    l, d = h.search(rows[7], 20)  # self query (src/net/web.rs:339)
+    assert l[0] == 8 and abs(d[0]) < 1e-3
