@@ -118,7 +118,7 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
     Cand mine = empty_cand();
     if (tid < kp) {
         mine = sm.s[tid];
-        sm.scan_score[tid] = mine.score;
+        sm.scan_score[tid] = mine.row != kNoRow ? mine.score : __int_as_float(0x7f800000);
         if (mine.row != kNoRow) {
             const uint4 *rp = reinterpret_cast<const uint4 *>(corpus + (size_t)mine.row * kDim);
             float acc = 0.0f;
@@ -172,7 +172,9 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
             // <= scan_min + eps and distance >= 1 - (scan_min + eps); it cannot displace or tie
             // the k-th result if that bound is strictly above the k-th distance.
             const float e = eps_q ? eps_q[qi] : eps;
-            const float bound = __fsub_rn(1.0f, __fadd_rn(sm.scan_score[kp - 1], e));
+            float scan_min = sm.scan_score[0];  // weakest kept candidate (lists need not be sorted)
+            for (int j = 1; j < kp; j++) scan_min = fminf(scan_min, sm.scan_score[j]);
+            const float bound = __fsub_rn(1.0f, __fadd_rn(scan_min, e));
             certified = bound > sm.kth_dist;
         }
         if (overflow && overflow[qi]) certified = false;  // candidates were lost: cannot certify

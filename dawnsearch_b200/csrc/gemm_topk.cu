@@ -20,9 +20,9 @@
 //              max-reduce, compare with the query's threshold (a register); survivors (rare)
 //              are appended to the query's candidate log in global memory.
 //
-// Selection across the corpus runs in geometrically growing ROUNDS of rows (1024, x4, ...):
+// Selection across the corpus runs in geometrically growing ROUNDS of rows (1024, x8, ...):
 // round 0 logs everything, select_topk_kernel then keeps the best k' per query and publishes
-// the k'-th score as the threshold for the next round, so a round appends ~3k' candidates per
+// the k'-th score as the threshold for the next round, so a round appends ~7k' candidates per
 // query regardless of its size.  The log is a superset of the top-k' under the fp16-query
 // scores; finalize.cu re-scores the k' survivors exactly and certifies the result with
 // eps_q = ||q - fp16(q)|| + accumulation slack (Cauchy-Schwarz, rows have norm <= 1.01).
@@ -45,7 +45,9 @@ constexpr int kABlockBytes = BM * BK * 2;   // 16384
 constexpr int kABytes = kABlockBytes * kKBlocks;  // 98304
 constexpr int kBStageBytes = BN * BK * 2;   // 32768
 constexpr int kTmemCols = 512;
-constexpr int kSmemBytes = 1024 + kABytes + kStagesB * kBStageBytes + 256;
+constexpr int kStageCap = 16;  // survivors a query thread parks in shared memory before one atomic flush
+constexpr int kStagingBytes = kStageCap * 128 * 8;  // 16 KB
+constexpr int kSmemBytes = 1024 + kABytes + kStagesB * kBStageBytes + 256 + kStagingBytes;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -127,8 +129,22 @@ struct GemmSmem {  // offsets from the 1024-aligned base
     static constexpr int a_off = 0;
     static constexpr int b_off = kABytes;
     static constexpr int bar_off = kABytes + kStagesB * kBStageBytes;
+    static constexpr int staging_off = bar_off + 256;
     // barriers (8 B each): full[3], empty[3], tmem_full[2], tmem_empty[2], a_full, a_free ; then tmem ptr
 };
+
+// Move a query thread's parked survivors to its global candidate log: one atomic reserves the
+// slots, the copies are plain stores.  stage is [kStageCap][128] uint2, column = epilogue thread.
+__device__ __noinline__ void flush_staged(uint32_t stage_smem, int col, uint32_t n, uint2 *__restrict__ log_q,
+                                          uint32_t *__restrict__ cnt_q, uint32_t *__restrict__ overflow_q, int cap) {
+    uint32_t slot = atomicAdd(cnt_q, n);
+    for (uint32_t e = 0; e < n; e++, slot++) {
+        uint2 val;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(val.x), "=r"(val.y) : "r"(stage_smem + (e * 128 + col) * 8));
+        if (slot < (uint32_t)cap) log_q[slot] = val;
+        else *overflow_q = 1u;
+    }
+}
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
@@ -252,6 +268,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     } else if (warp >= 4) {
         // ===================== epilogue: threshold filter =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+        const int col = quarter * 32 + lane;
+        const uint32_t stage_smem = base + GemmSmem::staging_off;
+        uint32_t n_st = 0;
         uint32_t tile_ctr = 0;
         for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int t = (int)(u % (uint32_t)n_qtiles);
@@ -268,40 +287,70 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 mbar_wait(tfull_bar(acc), (tile_ctr >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; c++) {
-                    uint32_t v[32];
-                    tc_ld_32x32b_x32(taddr + c * 32, v);
-                    tc_wait_ld();
-                    float m = __uint_as_float(v[0]);
+                const int lim_tile = (int)min(row_end, n_rows) - (int)row0;  // valid columns of this tile
+                // One 32-column chunk: 4 group maxima -> overall max; only groups that reach the
+                // threshold are examined element by element.  Survivors are parked in shared memory.
+                auto process = [&](const uint32_t (&v)[32], int c) {
+                    float g[4];
 #pragma unroll
-                    for (int i = 1; i < 32; i++) m = fmaxf(m, __uint_as_float(v[i]));
+                    for (int gi = 0; gi < 4; gi++) {
+                        float m0 = fmaxf(__uint_as_float(v[8 * gi]), __uint_as_float(v[8 * gi + 1]));
+                        float m1 = fmaxf(__uint_as_float(v[8 * gi + 2]), __uint_as_float(v[8 * gi + 3]));
+                        float m2 = fmaxf(__uint_as_float(v[8 * gi + 4]), __uint_as_float(v[8 * gi + 5]));
+                        float m3 = fmaxf(__uint_as_float(v[8 * gi + 6]), __uint_as_float(v[8 * gi + 7]));
+                        g[gi] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    }
+                    const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
                     if (q_valid && m >= thr) {
-                        // Survivors of this 32-column chunk: ONE atomic reserves their slots (a
-                        // single round trip for the whole warp), then the stores are fire-and-forget.
-                        const int lim = (int)min(row_end, n_rows) - (int)(row0 + c * 32);
-                        uint32_t mask = 0;
 #pragma unroll
-                        for (int i = 0; i < 32; i++) mask |= (__uint_as_float(v[i]) >= thr) ? (1u << i) : 0u;
-                        if (lim < 32) mask &= lim <= 0 ? 0u : ((1u << lim) - 1u);
-                        if (mask) {
-                            uint32_t slot = atomicAdd(cnt_g + q, (uint32_t)__popc(mask));
+                        for (int gi = 0; gi < 4; gi++) {
+                            if (g[gi] >= thr) {
 #pragma unroll
-                            for (int i = 0; i < 32; i++) {
-                                if (mask & (1u << i)) {
-                                    if (slot < (uint32_t)log_cap) log_q[slot] = make_uint2(v[i], row0 + c * 32 + i);
-                                    else overflow_g[q] = 1u;
-                                    slot++;
+                                for (int j = 0; j < 8; j++) {
+                                    const int i = 8 * gi + j;
+                                    if (__uint_as_float(v[i]) >= thr && c * 32 + i < lim_tile) {
+                                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(stage_smem + (n_st * 128 + col) * 8),
+                                                     "r"(v[i]), "r"(row0 + c * 32 + i)
+                                                     : "memory");
+                                        if (++n_st == (uint32_t)kStageCap) {
+                                            flush_staged(stage_smem, col, n_st, log_q, cnt_g + q, overflow_g + q, log_cap);
+                                            n_st = 0;
+                                        }
+                                    }
                                 }
                             }
                         }
                     }
                     __syncwarp();
+                };
+                // software pipeline: the next chunk's TMEM load is in flight while this one is filtered
+                uint32_t v0[32], v1[32];
+                tc_ld_32x32b_x32(taddr, v0);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c += 2) {
+                    tc_wait_ld();
+                    tc_ld_32x32b_x32(taddr + (c + 1) * 32, v1);
+                    process(v0, c);
+                    tc_wait_ld();
+                    if (c + 2 < BN / 32) tc_ld_32x32b_x32(taddr + (c + 2) * 32, v0);
+                    process(v1, c + 1);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
+                // Flush together: when any lane's park is half full, every lane with survivors
+                // flushes now, so the warp pays ONE atomic round trip instead of one per lane.
+                if (__any_sync(0xffffffffu, n_st >= (uint32_t)(kStageCap / 2))) {
+                    if (n_st) flush_staged(stage_smem, col, n_st, log_q, cnt_g + q, overflow_g + q, log_cap);
+                    n_st = 0;
+                    __syncwarp();
+                }
             }
+            if (n_st) {  // the next unit belongs to another query tile
+                flush_staged(stage_smem, col, n_st, log_q, cnt_g + q, overflow_g + q, log_cap);
+                n_st = 0;
+            }
+            __syncwarp();
         }
     }
 
@@ -342,7 +391,10 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float *__restri
 }
 
 // ---- select: keep the best k' log entries of a query, publish the k'-th score as threshold ----
-constexpr int kSelThreads = 256;  // enough for ~512 live entries per query; many CTAs per SM
+// 64-bit radix select (8 passes over a 256-bin shared histogram) on key = (ordered score, ~row):
+// descending key order == score descending, row ascending.  Keys are unique (rows are), so
+// exactly k' entries satisfy key >= K.  The kept entries are written back UNSORTED.
+constexpr int kSelThreads = 256;
 constexpr int kSelCap = 2048;  // == log capacity per query
 
 __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(uint2 *__restrict__ log_g, uint32_t *__restrict__ cnt_g,
@@ -351,58 +403,90 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(uint2 *__restr
                                                                   const uint64_t *__restrict__ labels,
                                                                   Cand *__restrict__ final_lists) {
     __shared__ unsigned long long keys[kSelCap];
+    __shared__ unsigned long long s_prefix;
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_need, s_out;
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
     uint2 *log_q = log_g + (size_t)q * log_cap;
     const uint32_t cnt = cnt_g[q];
     const int n = (int)min(cnt, (uint32_t)log_cap);
-    int P = 64;
-    while (P < n) P <<= 1;
-    // key: score descending then row ascending == one descending u64 compare; 0 = empty
-    for (int i = tid; i < P; i += kSelThreads) {
-        unsigned long long key = 0ull;
-        if (i < n) {
-            const uint2 e = log_q[i];
-            key = ((unsigned long long)float_to_ordered(__uint_as_float(e.x)) << 32) | (unsigned long long)(~e.y);
-        }
-        keys[i] = key;
+    for (int i = tid; i < n; i += kSelThreads) {
+        const uint2 e = log_q[i];
+        keys[i] = ((unsigned long long)float_to_ordered(__uint_as_float(e.x)) << 32) | (unsigned long long)(~e.y);
+    }
+    if (tid == 0) {
+        s_prefix = 0ull;
+        s_need = (uint32_t)kp;
+        s_out = 0u;
     }
     __syncthreads();
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = tid; i < P / 2; i += kSelThreads) {
-                const int lo = (i / stride) * (stride * 2) + (i % stride);
-                const int hi = lo + stride;
-                const bool desc = ((lo & size) == 0);
-                const unsigned long long a = keys[lo], b = keys[hi];
-                if ((a < b) == desc) {
-                    keys[lo] = b;
-                    keys[hi] = a;
+    unsigned long long K = 0ull;  // keep everything when there are fewer than k' entries
+    if (n >= kp) {
+        for (int byte = 7; byte >= 0; byte--) {
+            hist[tid] = 0u;  // kSelThreads == 256
+            __syncthreads();
+            const unsigned long long prefix = s_prefix;
+            for (int i = tid; i < n; i += kSelThreads) {
+                const unsigned long long key = keys[i];
+                if (byte == 7 || (key >> (8 * (byte + 1))) == prefix) atomicAdd(&hist[(uint32_t)(key >> (8 * byte)) & 0xFFu], 1u);
+            }
+            __syncthreads();
+            if (tid < 32) {  // digits from 255 down; lane L owns digits 255-8L .. 248-8L
+                uint32_t mine = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) mine += hist[255 - 8 * tid - j];
+                uint32_t incl = mine;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (tid >= off) incl += o;
+                }
+                const uint32_t need = s_need;
+                const uint32_t hit = __ballot_sync(0xffffffffu, incl >= need);
+                if (tid == __ffs(hit) - 1) {
+                    uint32_t cum = incl - mine;
+                    for (int j = 0; j < 8; j++) {
+                        const int d = 255 - 8 * tid - j;
+                        if (cum + hist[d] >= need) {
+                            s_prefix = (prefix << 8) | (unsigned long long)d;
+                            s_need = need - cum;
+                            break;
+                        }
+                        cum += hist[d];
+                    }
                 }
             }
             __syncthreads();
         }
+        K = s_prefix;
     }
-    const int keep = min(n, kp);
-    for (int i = tid; i < keep; i += kSelThreads) {
+    // compaction (order does not matter downstream)
+    for (int i = tid; i < n; i += kSelThreads) {
         const unsigned long long key = keys[i];
-        log_q[i] = make_uint2(__float_as_uint(ordered_to_float((uint32_t)(key >> 32))), ~(uint32_t)key);
-    }
-    if (final_lists) {
-        for (int i = tid; i < kp; i += kSelThreads) {
-            Cand c = empty_cand();
-            if (i < keep) {
-                const unsigned long long key = keys[i];
-                c.score = ordered_to_float((uint32_t)(key >> 32));
-                c.row = ~(uint32_t)key;
-                c.label = labels[c.row];
+        if (key >= K) {
+            const uint32_t pos = atomicAdd(&s_out, 1u);
+            if (pos < (uint32_t)kp) {
+                const float sc = ordered_to_float((uint32_t)(key >> 32));
+                const uint32_t row = ~(uint32_t)key;
+                log_q[pos] = make_uint2(__float_as_uint(sc), row);
+                if (final_lists) {
+                    Cand c;
+                    c.score = sc;
+                    c.row = row;
+                    c.label = labels[row];
+                    final_lists[(size_t)q * kp + pos] = c;
+                }
             }
-            final_lists[(size_t)q * kp + i] = c;
         }
     }
+    __syncthreads();
+    const int keep = min(n, kp);
+    if (final_lists)
+        for (int i = keep + tid; i < kp; i += kSelThreads) final_lists[(size_t)q * kp + i] = empty_cand();
     if (tid == 0) {
         cnt_g[q] = (uint32_t)keep;
-        thr_g[q] = keep == kp ? ordered_to_float((uint32_t)(keys[kp - 1] >> 32)) : __int_as_float(0xff800000);
+        thr_g[q] = n >= kp ? ordered_to_float((uint32_t)(K >> 32)) : __int_as_float(0xff800000);
         if (cnt > (uint32_t)log_cap) overflow_g[q] = 1u;
     }
 }
@@ -486,10 +570,11 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
         select_topk_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, thr, overflow, kSelCap, p.kprime, p.labels, nullptr);
     }
     int launches = 2;
-    // rounds of rows: [0,1024), then x4 each time; every boundary is a multiple of the tile height
+    // rounds of rows: [0,1024), then x8 each time (~7k' survivors per query per round); every
+    // boundary is a multiple of the tile height
     uint64_t begin = 0, end = 1024;
     while (begin < p.n_rows) {
-        if (end > p.n_rows || end * 2 > p.n_rows) end = p.n_rows;  // fold a short last round into this one
+        if (end > p.n_rows || end + end / 4 > p.n_rows) end = p.n_rows;  // fold a short last round into this one
         const uint64_t n_tiles = (end - begin + BN - 1) / BN;
         uint64_t chunk = (n_tiles * (uint64_t)n_qtiles + (uint64_t)p.grid * 4 - 1) / ((uint64_t)p.grid * 4);
         if (chunk < 1) chunk = 1;
@@ -502,7 +587,7 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
                                                       last ? p.final_lists : nullptr);
         launches += 2;
         begin = end;
-        end = end * 4;
+        end = end * 8;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (p.eps_out) *p.eps_out = eps_q;
