@@ -89,6 +89,7 @@ struct dawn_index {
     int64_t gemm_small_batch = 3;          // from this batch size on, big corpora also take the tensor path
     int64_t gemm_small_batch_rows = 2000000;
     int64_t force_path = 0;  // 0 auto, 1 scan only, 2 gemm whenever possible
+    int64_t gemm_cta_group = 0;  // 0 auto, 1 = one CTA per tile, 2 = CTA pairs
 
     bool profiling = false;
     std::vector<EventPair> pending;
@@ -260,7 +261,7 @@ int search_enqueue(dawn_index *idx, const float *d_queries, size_t batch, size_t
                            ((int64_t)batch >= idx->gemm_min_batch && (int64_t)idx->size >= idx->gemm_min_rows) ||
                            ((int64_t)batch >= idx->gemm_small_batch && (int64_t)idx->size >= idx->gemm_small_batch_rows));
     if (use_gemm) {
-        const size_t qp = (batch + 127) / 128 * 128;
+        const size_t qp = (batch + 255) / 256 * 256;
         const size_t need_ws = gemm_workspace_bytes((int)batch);
         if (need_ws > idx->gemm_ws_cap) {
             if (idx->d_gemm_ws) cudaFree(idx->d_gemm_ws);
@@ -287,6 +288,7 @@ int search_enqueue(dawn_index *idx, const float *d_queries, size_t batch, size_t
         gs.n_queries = (int)batch;
         gs.kprime = kprime;
         gs.grid = grid;
+        gs.cta_group = (int)idx->gemm_cta_group;
         gs.workspace = idx->d_gemm_ws;
         gs.final_lists = idx->d_partials;
         gs.accum_slack = kGemmAccumSlack;
@@ -793,6 +795,7 @@ int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value) {
     else if (!strcmp(key, "gemm_small_batch")) idx->gemm_small_batch = value;
     else if (!strcmp(key, "gemm_small_batch_rows")) idx->gemm_small_batch_rows = value;
     else if (!strcmp(key, "force_path")) idx->force_path = value;
+    else if (!strcmp(key, "gemm_cta_group")) idx->gemm_cta_group = value;
     else return fail(DAWN_ERR_INVALID, "unknown option '%s'", key);
     return DAWN_OK;
 }

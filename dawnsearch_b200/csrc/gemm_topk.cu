@@ -40,14 +40,14 @@ constexpr int BN = 256;      // corpus rows per tile (UMMA N)
 constexpr int BK = 64;       // fp16 elements per k-block = 128 B = one swizzle atom row
 constexpr int kKBlocks = kDim / BK;  // 6
 constexpr int kUmmaK = 16;
-constexpr int kStagesB = 3;
+constexpr int kMaxStagesB = 6;              // 3 x 32 KB (one CTA) or 6 x 16 KB (CTA pair)
+constexpr int kBRingBytes = 3 * BN * BK * 2;  // 98304 either way
 constexpr int kABlockBytes = BM * BK * 2;   // 16384
 constexpr int kABytes = kABlockBytes * kKBlocks;  // 98304
-constexpr int kBStageBytes = BN * BK * 2;   // 32768
 constexpr int kTmemCols = 512;
 constexpr int kStageCap = 16;  // survivors a query thread parks in shared memory before one atomic flush
 constexpr int kStagingBytes = kStageCap * 128 * 8;  // 16 KB
-constexpr int kSmemBytes = 1024 + kABytes + kStagesB * kBStageBytes + 256 + kStagingBytes;
+constexpr int kSmemBytes = 1024 + kABytes + kBRingBytes + 256 + kStagingBytes;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -111,6 +111,52 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[3
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants ----------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) inside CTA `rank`
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; completion bytes are counted on the LEADER's barrier.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1,
+                                                 uint32_t leader_bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(leader_bar_cluster_addr)
+        : "memory");
+}
+// commit of the pair's MMAs: one arrival on the same barrier in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Shared-memory matrix descriptor for a K-major operand stored as rows of 128 B with the TMA
 // 128-byte swizzle: 8-row groups are 1024 B apart (SBO), version 1 (Blackwell), layout 2.
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
@@ -122,15 +168,16 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
     return d;
 }
-// Instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24.
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// Instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+// (M = 128 for one CTA, 256 for a CTA pair).
+__host__ __device__ constexpr uint32_t make_idesc(int m) { return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
 
 struct GemmSmem {  // offsets from the 1024-aligned base
     static constexpr int a_off = 0;
     static constexpr int b_off = kABytes;
-    static constexpr int bar_off = kABytes + kStagesB * kBStageBytes;
+    static constexpr int bar_off = kABytes + kBRingBytes;
     static constexpr int staging_off = bar_off + 256;
-    // barriers (8 B each): full[3], empty[3], tmem_full[2], tmem_empty[2], a_full, a_free ; then tmem ptr
+    // barriers (8 B each): full[6], empty[6], tmem_full[2], tmem_empty[2], a_full, a_free ; then tmem ptr
 };
 
 // Move a query thread's parked survivors to its global candidate log: one atomic reserves the
@@ -146,26 +193,37 @@ __device__ __noinline__ void flush_staged(uint32_t stage_smem, int col, uint32_t
     }
 }
 
+// CG = 1: one CTA per tile (M = 128 queries).  CG = 2: a CTA pair shares every MMA (cta_group::2,
+// M = 256 queries, each CTA holds 128 of them and streams only HALF of each 256-row corpus tile),
+// which halves the L2->shared traffic per SM -- the bound of the one-CTA kernel at large batch.
+template <int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                  uint32_t row_begin, uint32_t row_end, uint32_t n_rows, int n_qtiles, int n_queries,
                  int chunk_tiles, const float *__restrict__ thr_g, uint32_t *__restrict__ cnt_g,
                  uint2 *__restrict__ log_g, uint32_t *__restrict__ overflow_g, int log_cap) {
+    constexpr int kStagesB = 3 * CG;
+    constexpr int kBRows = BN / CG;                 // corpus rows this CTA streams per tile
+    constexpr int kBStageBytes = kBRows * BK * 2;   // 32 KB or 16 KB
+    constexpr uint32_t kIdesc = make_idesc(BM * CG);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_smem = base + GemmSmem::a_off;
     const uint32_t b_smem = base + GemmSmem::b_off;
     const uint32_t bars = base + GemmSmem::bar_off;
     auto full_bar = [&](int s) { return bars + 8 * s; };
-    auto empty_bar = [&](int s) { return bars + 8 * (3 + s); };
-    auto tfull_bar = [&](int a) { return bars + 8 * (6 + a); };
-    auto tempty_bar = [&](int a) { return bars + 8 * (8 + a); };
-    const uint32_t a_full_bar = bars + 8 * 10;
-    const uint32_t a_free_bar = bars + 8 * 11;
-    const uint32_t tmem_ptr_smem = bars + 8 * 12;
+    auto empty_bar = [&](int s) { return bars + 8 * (kMaxStagesB + s); };
+    auto tfull_bar = [&](int a) { return bars + 8 * (2 * kMaxStagesB + a); };
+    auto tempty_bar = [&](int a) { return bars + 8 * (2 * kMaxStagesB + 2 + a); };
+    const uint32_t a_full_bar = bars + 8 * (2 * kMaxStagesB + 4);
+    const uint32_t a_free_bar = bars + 8 * (2 * kMaxStagesB + 5);
+    const uint32_t tmem_ptr_smem = bars + 8 * (2 * kMaxStagesB + 6);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+    const uint32_t unit_first = blockIdx.x / CG;                 // CTA pairs walk the units together
+    const uint32_t unit_stride = gridDim.x / CG;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStagesB; s++) {
@@ -174,19 +232,26 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+            mbar_init(tempty_bar(a), 4 * CG);  // one arrival per epilogue warp (of both CTAs)
         }
         mbar_init(a_full_bar, 1);
         mbar_init(a_free_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM allocation: one full warp, all 512 columns (1 CTA per SM)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_smem),
-                     "r"((uint32_t)kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (warp == 1) {  // TMEM allocation: one full warp (the same warp in both CTAs of a pair), all 512 columns
+        if constexpr (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_smem),
+                         "r"((uint32_t)kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_smem),
+                         "r"((uint32_t)kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
@@ -198,40 +263,56 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t n_units = n_chunks * (uint32_t)n_qtiles;
 
     if (warp == 0 && lane == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (both CTAs of a pair) =====================
+        // Pair mode: every load signals the LEADER's barrier; only the leader posts the expected
+        // byte count (for both CTAs); each CTA waits for its own copy of the empty barriers, which
+        // the MMA commit multicasts.
         uint32_t g = 0;         // B stage counter
         uint32_t n_reload = 0;  // A (query tile) loads issued by this CTA
         int cur_t = -1;
-        for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        for (uint32_t u = unit_first; u < n_units; u += unit_stride) {
             const int t = (int)(u % (uint32_t)n_qtiles);
             const uint32_t chunk = u / (uint32_t)n_qtiles;
             if (t != cur_t) {
                 // the MMAs that read the previous query tile must have retired (a_free is committed
                 // by the MMA warp exactly when the next unit needs a different tile)
                 if (n_reload > 0) mbar_wait(a_free_bar, (n_reload - 1) & 1u);
-                mbar_expect_tx(a_full_bar, kABytes);
-                for (int kb = 0; kb < kKBlocks; kb++)
-                    tma_load_2d(a_smem + kb * kABlockBytes, &tmap_q, kb * BK, t * BM, a_full_bar);
+                const int qrow = t * BM * CG + (int)cta_rank * BM;
+                if constexpr (CG == 2) {
+                    if (cta_rank == 0) mbar_expect_tx(a_full_bar, 2 * kABytes);
+                    const uint32_t lead = mapa_rank(a_full_bar, 0);
+                    for (int kb = 0; kb < kKBlocks; kb++)
+                        tma_load_2d_pair(a_smem + kb * kABlockBytes, &tmap_q, kb * BK, qrow, lead);
+                } else {
+                    mbar_expect_tx(a_full_bar, kABytes);
+                    for (int kb = 0; kb < kKBlocks; kb++)
+                        tma_load_2d(a_smem + kb * kABlockBytes, &tmap_q, kb * BK, qrow, a_full_bar);
+                }
                 cur_t = t;
                 n_reload++;
             }
             const uint32_t tile0 = chunk * chunk_tiles;
             const uint32_t tile1 = min(n_tiles, tile0 + chunk_tiles);
             for (uint32_t tile = tile0; tile < tile1; tile++) {
-                const int row0 = (int)(row_begin + tile * BN);
+                const int row0 = (int)(row_begin + tile * BN) + (int)cta_rank * kBRows;
                 for (int kb = 0; kb < kKBlocks; kb++, g++) {
                     const uint32_t s = g % kStagesB;
                     mbar_wait(empty_bar(s), ((g / kStagesB) & 1u) ^ 1u);
-                    mbar_expect_tx(full_bar(s), kBStageBytes);
-                    tma_load_2d(b_smem + s * kBStageBytes, &tmap_x, kb * BK, row0, full_bar(s));
+                    if constexpr (CG == 2) {
+                        if (cta_rank == 0) mbar_expect_tx(full_bar(s), 2 * kBStageBytes);
+                        tma_load_2d_pair(b_smem + s * kBStageBytes, &tmap_x, kb * BK, row0, mapa_rank(full_bar(s), 0));
+                    } else {
+                        mbar_expect_tx(full_bar(s), kBStageBytes);
+                        tma_load_2d(b_smem + s * kBStageBytes, &tmap_x, kb * BK, row0, full_bar(s));
+                    }
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+        // ===================== MMA issuer (leader CTA only) =====================
         uint32_t g = 0, tile_ctr = 0, a_loads = 0;
         int cur_t = -1;
-        for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        for (uint32_t u = unit_first; u < n_units; u += unit_stride) {
             const int t = (int)(u % (uint32_t)n_qtiles);
             const uint32_t chunk = u / (uint32_t)n_qtiles;
             if (t != cur_t) {
@@ -255,15 +336,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / kUmmaK; k++) {
                         // advance 16 elements = 32 B inside the swizzle atom: +2 in 16-byte units
-                        tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
-                                   (uint32_t)((kb | k) != 0));
+                        if constexpr (CG == 2)
+                            tc_mma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
+                                            (uint32_t)((kb | k) != 0));
+                        else
+                            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
+                                       (uint32_t)((kb | k) != 0));
                     }
-                    tc_commit(empty_bar(s));  // stage free once these MMAs retire
+                    if constexpr (CG == 2) tc_commit_pair(empty_bar(s));  // stage free in both CTAs
+                    else tc_commit(empty_bar(s));
                 }
-                tc_commit(tfull_bar(acc));    // accumulator ready for the epilogue
+                if constexpr (CG == 2) tc_commit_pair(tfull_bar(acc));  // accumulators ready in both CTAs
+                else tc_commit(tfull_bar(acc));
             }
-            const uint32_t u_next = u + gridDim.x;
-            if (u_next < n_units && (int)(u_next % (uint32_t)n_qtiles) != t) tc_commit(a_free_bar);
+            const uint32_t u_next = u + unit_stride;
+            if (u_next < n_units && (int)(u_next % (uint32_t)n_qtiles) != t) {
+                if constexpr (CG == 2) tc_commit_pair(a_free_bar);
+                else tc_commit(a_free_bar);
+            }
         }
     } else if (warp >= 4) {
         // ===================== epilogue: threshold filter =====================
@@ -272,10 +362,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const uint32_t stage_smem = base + GemmSmem::staging_off;
         uint32_t n_st = 0;
         uint32_t tile_ctr = 0;
-        for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const uint32_t tempty_lead0 = CG == 2 ? mapa_rank(tempty_bar(0), 0) : 0u;  // the MMA issuer waits on the leader's
+        const uint32_t tempty_lead1 = CG == 2 ? mapa_rank(tempty_bar(1), 0) : 0u;
+        for (uint32_t u = unit_first; u < n_units; u += unit_stride) {
             const int t = (int)(u % (uint32_t)n_qtiles);
             const uint32_t chunk = u / (uint32_t)n_qtiles;
-            const int q = t * BM + quarter * 32 + lane;
+            const int q = t * BM * CG + (int)cta_rank * BM + quarter * 32 + lane;
             const bool q_valid = q < n_queries;
             const float thr = q_valid ? thr_g[q] : __int_as_float(0x7f800000);
             uint2 *log_q = log_g + (size_t)q * log_cap;
@@ -337,7 +429,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                if (lane == 0) {
+                    if constexpr (CG == 2) mbar_arrive_cluster(acc ? tempty_lead1 : tempty_lead0);
+                    else mbar_arrive(tempty_bar(acc));
+                }
                 // Flush together: when any lane's park is half full, every lane with survivors
                 // flushes now, so the warp pays ONE atomic round trip instead of one per lane.
                 if (__any_sync(0xffffffffu, n_st >= (uint32_t)(kStageCap / 2))) {
@@ -355,11 +450,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // the peer may still be reading this CTA's operands / barriers
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         __syncwarp();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
+        if constexpr (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
     }
 }
 
@@ -526,14 +625,41 @@ bool make_tmap(CUtensorMap *map, const void *base, uint64_t rows, uint32_t box_r
 }  // namespace
 
 size_t gemm_workspace_bytes(int n_queries) {
-    const size_t qp = ((size_t)n_queries + BM - 1) / BM * BM;
+    const size_t qp = ((size_t)n_queries + 2 * BM - 1) / (2 * BM) * (2 * BM);  // pair mode pads to 256
     return qp * kDim * sizeof(__half) + qp * (4 * sizeof(float)) + qp * (size_t)kSelCap * sizeof(uint2) + 1024;
+}
+
+template <int CG>
+static cudaError_t launch_gemm_round(int grid, cudaStream_t s, const CUtensorMap &tmap_q, const CUtensorMap &tmap_x,
+                                     uint32_t begin, uint32_t end, uint32_t n_rows, int n_qtiles, int n_queries, int chunk,
+                                     const float *thr, uint32_t *cnt, uint2 *log, uint32_t *overflow) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int log_cap = kSelCap;
+    return cudaLaunchKernelEx(&cfg, gemm_topk_kernel<CG>, tmap_q, tmap_x, begin, end, n_rows, n_qtiles, n_queries, chunk,
+                              thr, cnt, log, overflow, log_cap);
 }
 
 cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
     if (p.n_queries <= 0 || p.n_rows == 0) return cudaErrorInvalidValue;
-    const int qp = (p.n_queries + BM - 1) / BM * BM;
-    const int n_qtiles = qp / BM;
+    // CTA pairs (cta_group::2, 256-query tiles) once there is more than one 128-query tile
+    int cg = p.cta_group;
+    if (cg != 1 && cg != 2) cg = p.n_queries > BM ? 2 : 1;
+    if (p.grid % 2) cg = 1;
+    const int qtile = BM * cg;
+    const int qp = (p.n_queries + qtile - 1) / qtile * qtile;
+    const int n_qtiles = qp / qtile;
+    const int workers = p.grid / cg;
     // carve the workspace
     uint8_t *w = static_cast<uint8_t *>(p.workspace);
     __half *q16 = reinterpret_cast<__half *>(w);
@@ -553,12 +679,14 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gemm_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
     CUtensorMap tmap_q, tmap_x;
-    if (!make_tmap(&tmap_q, q16, (uint64_t)qp, BM) || !make_tmap(&tmap_x, p.corpus, p.n_rows, BN))
+    if (!make_tmap(&tmap_q, q16, (uint64_t)qp, BM) || !make_tmap(&tmap_x, p.corpus, p.n_rows, BN / cg))
         return cudaErrorInvalidValue;
 
     cudaError_t e;
@@ -576,12 +704,16 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
     while (begin < p.n_rows) {
         if (end > p.n_rows || end + end / 4 > p.n_rows) end = p.n_rows;  // fold a short last round into this one
         const uint64_t n_tiles = (end - begin + BN - 1) / BN;
-        uint64_t chunk = (n_tiles * (uint64_t)n_qtiles + (uint64_t)p.grid * 4 - 1) / ((uint64_t)p.grid * 4);
+        uint64_t chunk = (n_tiles * (uint64_t)n_qtiles + (uint64_t)workers * 4 - 1) / ((uint64_t)workers * 4);
         if (chunk < 1) chunk = 1;
         if (chunk > 64) chunk = 64;
-        gemm_topk_kernel<<<p.grid, kGemmThreads, kSmemBytes, s>>>(tmap_q, tmap_x, (uint32_t)begin, (uint32_t)end,
-                                                                  (uint32_t)p.n_rows, n_qtiles, p.n_queries, (int)chunk,
-                                                                  thr, cnt, log, overflow, kSelCap);
+        if (cg == 2)
+            e = launch_gemm_round<2>(p.grid, s, tmap_q, tmap_x, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows, n_qtiles,
+                                     p.n_queries, (int)chunk, thr, cnt, log, overflow);
+        else
+            e = launch_gemm_round<1>(p.grid, s, tmap_q, tmap_x, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows, n_qtiles,
+                                     p.n_queries, (int)chunk, thr, cnt, log, overflow);
+        if (e != cudaSuccess) return e;
         const bool last = end >= p.n_rows;
         select_topk_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, thr, overflow, kSelCap, p.kprime, p.labels,
                                                       last ? p.final_lists : nullptr);
