@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--rows", type=int, default=100_000_000, help="total corpus rows (all GPUs)")
     ap.add_argument("--batch", type=int, default=1024, help="queries per step")
     ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--scalar", default="f16", choices=["f16", "i8"], help="stored precision of the corpus")
     ap.add_argument("--latency-steps", type=int, default=30, help="batch-1 steps for the latency section (0 = skip)")
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -149,7 +150,8 @@ def cpu_arm(args, steps, warmup, rows_total):
 
 
 def workload_name(args):
-    return (f"exact top-{args.k} over {args.rows} x 384 fp16 (synthetic unit vectors), batch {args.batch} "
+    return (f"exact top-{args.k} over {args.rows} x 384 {'fp16' if args.scalar == 'f16' else 'int8 (+f32 scale per vector)'} "
+            f"(synthetic unit vectors), batch {args.batch} "
             f"per step, corpus sharded by id range over {args.gpus} GPU(s)")
 
 
@@ -191,7 +193,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
 
     first, n_local = shard_range(rank, world, args.rows)
-    sh = ShardedIndex(local, max(n_local, 1))
+    row_bytes = ROW_BYTES if args.scalar == "f16" else 388  # i8: 384 B + f32 scale
+    sh = ShardedIndex(local, max(n_local, 1), quantization=0 if args.scalar == "f16" else 1)
     t0 = time.perf_counter()
     sh.index.add_synthetic(SEED, first, n_local)
     fill_s = time.perf_counter() - t0
@@ -267,12 +270,12 @@ def run_ours(args):
                     "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "frac_of_burst_peak": ach / peaks["tf_burst"], "frac_of_nominal_2250": ach / 2250.0,
                     "algorithmic_flops_per_batch": flops, "avg_batch_ms": gms,
-                    "corpus_stream_gbps": n_local * ROW_BYTES / (gms / 1e3) / 1e9}
+                    "corpus_stream_gbps": n_local * row_bytes / (gms / 1e3) / 1e9}
         launches = max(int(prof["scan_launches"]), 1)
         sms = prof["scan_ms"] / launches
-        algo = n_local * ROW_BYTES
+        algo = n_local * row_bytes
         ach = algo / (sms / 1e3) / 1e9 if sms > 0 else 0.0
-        return {"bound": "hbm", "kernel": "scan_topk_f16_kernel", "achieved": ach, "peak": peaks["hbm"],
+        return {"bound": "hbm", "kernel": "scan_topk_f16_kernel" if args.scalar == "f16" else "scan_topk_i8_kernel", "achieved": ach, "peak": peaks["hbm"],
                 "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
                 "peak_source": peaks["source"] + " hbm_gbs", "frac_of_nominal_8TBs": ach / 8000.0,
                 "algorithmic_bytes_per_launch": algo, "avg_launch_ms": sms, "launches_timed": int(prof["scan_launches"])}

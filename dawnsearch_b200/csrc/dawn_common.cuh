@@ -17,6 +17,8 @@ namespace dawn {
 constexpr int kDim = 384;                       // EM_LEN, src/search/vector.rs:26
 constexpr int kRowBytesF16 = kDim * 2;          // 768 B per stored fp16 page vector
 constexpr int kMaxCand = 128;                   // largest candidate-list length (k + slack)
+constexpr int kI8BlockRows = 8;                 // int8 storage: 8 rows of 384 int8, then their 8 f32 scales
+constexpr int kI8BlockBytes = kI8BlockRows * kDim + kI8BlockRows * 4;  // 3,104 (a multiple of 16 for TMA)
 constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 constexpr uint64_t kNoLabel = 0xFFFFFFFFFFFFFFFFull;
 
@@ -117,12 +119,50 @@ struct FinalizeLaunch {
     float *distances_out;   // [nq][k]
     uint32_t *counts_out;   // [nq]
     uint32_t *flags_out;    // [nq] bit0 = exactness certified
+    int scalar;             // 0 = fp16 rows (corpus is __half*), 1 = blocked int8 arena (corpus is uint8_t*)
     const float *eps_q;     // optional per-query eps (GEMM path: depends on the query's fp16 rounding)
     const uint32_t *overflow;  // optional per-query "candidate log overflowed" flags -> not certified
 };
 // K5+K6: merge per-CTA lists, re-score candidates in the reference's order of summation
 // (src/search/vector.rs:128-134), final order and 1 - score.
 cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s);
+
+// ---- int8 storage (K4) ----
+// A query prepared for the int8 scan: q ~= s1*hi + s2*lo.
+struct __align__(16) I8Query {
+    int8_t hi[kDim];
+    int8_t lo[kDim];
+    float s1, s2;
+    float pad_[2];
+};
+__host__ __device__ inline size_t i8_row_offset(size_t row) {
+    return (row / kI8BlockRows) * (size_t)kI8BlockBytes + (row % kI8BlockRows) * (size_t)kDim;
+}
+__host__ __device__ inline size_t i8_scale_offset(size_t row) {
+    return (row / kI8BlockRows) * (size_t)kI8BlockBytes + (size_t)kI8BlockRows * kDim + (row % kI8BlockRows) * 4;
+}
+__host__ __device__ inline size_t i8_arena_bytes(size_t rows) {
+    return (rows + kI8BlockRows - 1) / kI8BlockRows * (size_t)kI8BlockBytes;
+}
+struct ScanLaunchI8 {
+    const uint8_t *corpus;    // blocked int8 arena
+    const uint64_t *labels;
+    uint32_t n_rows;
+    const I8Query *queries;   // [nq] prepared queries, device
+    int nq;                   // 1 or 2
+    int kprime;
+    Cand *partials;           // [nq][grid][kprime]
+    uint32_t *chunk_counter;
+    uint32_t *status;
+    int grid;
+};
+cudaError_t launch_scan_topk_i8(const ScanLaunchI8 &p, cudaStream_t s);
+cudaError_t launch_prep_queries_i8(const float *q32, int n_queries, I8Query *out, float *eps_q, cudaStream_t s);
+// f32 rows -> blocked int8 arena at rows [first_row, first_row+n) (per-row absmax/127 scale).
+cudaError_t launch_ingest_i8(const float *src_f32, uint8_t *arena, size_t first_row, size_t n_rows, cudaStream_t s);
+cudaError_t launch_synth_i8(uint8_t *arena, size_t dst_first_row, uint64_t seed, uint64_t first_row, size_t n_rows,
+                            cudaStream_t s);
+cudaError_t launch_gather_f32_i8(const uint8_t *arena, const uint32_t *rows, size_t n, float *out, cudaStream_t s);
 
 struct GemmSearch {
     const __half *corpus;     // [n_rows][384] fp16

@@ -56,7 +56,8 @@ struct dawn_index {
     cudaStream_t stream = nullptr;
     bool dead = false;  // sticky CUDA failure
 
-    __half *corpus = nullptr;
+    int scalar = DAWN_SCALAR_F16;  // storage of the corpus: fp16 rows or the blocked int8 arena
+    __half *corpus = nullptr;      // fp16: [phys][384]; int8: the same pointer holds the blocked arena
     uint64_t *labels = nullptr;
     size_t size = 0;      // rows committed to the device
     size_t capacity = 0;  // logical capacity promised to the caller
@@ -155,6 +156,11 @@ void end_event(dawn_index *idx, EventPair &p, cudaStream_t s) {
     idx->pending.push_back(p);
 }
 
+inline size_t arena_bytes(const dawn_index *idx, size_t rows) {
+    return idx->scalar == DAWN_SCALAR_I8 ? i8_arena_bytes(rows) : rows * (size_t)kRowBytesF16;
+}
+inline uint8_t *arena_i8(const dawn_index *idx) { return reinterpret_cast<uint8_t *>(idx->corpus); }
+
 int grow_physical(dawn_index *idx, size_t rows) {
     if (rows <= idx->phys) return DAWN_OK;
     if (rows > 0xFFFFFFF0ull) return fail(DAWN_ERR_INVALID, "capacity %zu exceeds 2^32 rows per GPU", rows);
@@ -165,16 +171,16 @@ int grow_physical(dawn_index *idx, size_t rows) {
     }
     __half *nc = nullptr;
     uint64_t *nl = nullptr;
-    cudaError_t e = cudaMalloc(&nc, want * kRowBytesF16);
+    cudaError_t e = cudaMalloc(&nc, arena_bytes(idx, want));
     if (e != cudaSuccess && want > rows) {
         cudaGetLastError();
         want = rows;
-        e = cudaMalloc(&nc, want * kRowBytesF16);
+        e = cudaMalloc(&nc, arena_bytes(idx, want));
     }
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(DAWN_ERR_CAPACITY, "cannot allocate %zu bytes of HBM for %zu vectors: %s",
-                    want * (size_t)kRowBytesF16, want, cudaGetErrorString(e));
+                    arena_bytes(idx, want), want, cudaGetErrorString(e));
     }
     e = cudaMalloc(&nl, want * sizeof(uint64_t));
     if (e != cudaSuccess) {
@@ -183,7 +189,7 @@ int grow_physical(dawn_index *idx, size_t rows) {
         return fail(DAWN_ERR_CAPACITY, "cannot allocate label table for %zu vectors", want);
     }
     if (idx->size > 0) {
-        CK(idx, cudaMemcpyAsync(nc, idx->corpus, idx->size * kRowBytesF16, cudaMemcpyDeviceToDevice, idx->stream));
+        CK(idx, cudaMemcpyAsync(nc, idx->corpus, arena_bytes(idx, idx->size), cudaMemcpyDeviceToDevice, idx->stream));
         CK(idx, cudaMemcpyAsync(nl, idx->labels, idx->size * sizeof(uint64_t), cudaMemcpyDeviceToDevice, idx->stream));
         CK(idx, cudaStreamSynchronize(idx->stream));
     }
@@ -200,7 +206,8 @@ int flush_staged(dawn_index *idx) {
     if (idx->staged == 0) return DAWN_OK;
     const size_t n = idx->staged;
     CK(idx, cudaMemcpyAsync(idx->d_stage, idx->h_stage, n * kDim * sizeof(float), cudaMemcpyHostToDevice, idx->stream));
-    CK(idx, launch_ingest_f16(idx->d_stage, idx->corpus + idx->size * kDim, n, idx->stream));
+    if (idx->scalar == DAWN_SCALAR_I8) CK(idx, launch_ingest_i8(idx->d_stage, arena_i8(idx), idx->size, n, idx->stream));
+    else CK(idx, launch_ingest_f16(idx->d_stage, idx->corpus + idx->size * kDim, n, idx->stream));
     idx->prof.kernel_launches++;
     CK(idx, cudaMemcpyAsync(idx->labels + idx->size, idx->h_stage_labels, n * sizeof(uint64_t), cudaMemcpyHostToDevice, idx->stream));
     CK(idx, cudaStreamSynchronize(idx->stream));
@@ -255,6 +262,84 @@ int search_enqueue(dawn_index *idx, const float *d_queries, size_t batch, size_t
                    uint64_t *d_labels_out, float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags,
                    cudaStream_t s, bool scan_only = false) {
     const int grid = idx->sm_count;
+    if (idx->scalar == DAWN_SCALAR_I8) {
+        // K4: int8 storage -> streaming dp4a scan, 1 or 2 queries per pass, exact f32 re-score
+        const size_t need_ws = batch * (sizeof(I8Query) + sizeof(float)) + 256;
+        if (need_ws > idx->gemm_ws_cap) {
+            if (idx->d_gemm_ws) cudaFree(idx->d_gemm_ws);
+            idx->gemm_ws_cap = 0;
+            CK(idx, cudaMalloc(&idx->d_gemm_ws, need_ws));
+            idx->gemm_ws_cap = need_ws;
+        }
+        I8Query *d_iq = static_cast<I8Query *>(idx->d_gemm_ws);
+        float *d_eps = reinterpret_cast<float *>(static_cast<uint8_t *>(idx->d_gemm_ws) + batch * sizeof(I8Query));
+        const size_t need_partials = batch * (size_t)grid * kprime;
+        if (need_partials > idx->partials_cap) {
+            if (idx->d_partials) cudaFree(idx->d_partials);
+            idx->partials_cap = 0;
+            CK(idx, cudaMalloc(&idx->d_partials, need_partials * sizeof(Cand)));
+            idx->partials_cap = need_partials;
+        }
+        const size_t need_counters = batch + 1;
+        if (need_counters > idx->counters_cap) {
+            size_t cap = need_counters < 1024 ? 1024 : need_counters;
+            if (idx->d_counters) cudaFree(idx->d_counters);
+            idx->counters_cap = 0;
+            CK(idx, cudaMalloc(&idx->d_counters, cap * sizeof(uint32_t)));
+            idx->counters_cap = cap;
+        }
+        CK(idx, cudaMemsetAsync(idx->d_counters, 0, need_counters * sizeof(uint32_t), s));
+        CK(idx, launch_prep_queries_i8(d_queries, (int)batch, d_iq, d_eps, s));
+        idx->prof.kernel_launches++;
+        size_t done = 0, pass = 0;
+        while (done < batch) {
+            const int qt = batch - done >= 2 ? 2 : 1;
+            ScanLaunchI8 sl;
+            sl.corpus = arena_i8(idx);
+            sl.labels = idx->labels;
+            sl.n_rows = (uint32_t)idx->size;
+            sl.queries = d_iq + done;
+            sl.nq = qt;
+            sl.kprime = kprime;
+            sl.partials = idx->d_partials + done * (size_t)grid * kprime;
+            sl.chunk_counter = idx->d_counters + 1 + pass;
+            sl.status = idx->d_counters;
+            sl.grid = grid;
+            EventPair ev;
+            bool timed = begin_event(idx, 0, s, &ev);
+            CK(idx, launch_scan_topk_i8(sl, s));
+            if (timed) end_event(idx, ev, s);
+            idx->prof.scan_launches++;
+            idx->prof.kernel_launches++;
+            done += qt;
+            pass++;
+        }
+        FinalizeLaunch fl;
+        fl.corpus = idx->corpus;
+        fl.queries = d_queries;
+        fl.nq = (int)batch;
+        fl.partials = idx->d_partials;
+        fl.n_lists = grid;
+        fl.kprime = kprime;
+        fl.k = (int)k;
+        fl.eps = 0.f;
+        fl.labels_out = d_labels_out;
+        fl.distances_out = d_dist_out;
+        fl.counts_out = d_counts;
+        fl.flags_out = d_flags;
+        fl.scalar = 1;
+        fl.eps_q = d_eps;
+        fl.overflow = nullptr;
+        EventPair ev;
+        bool timed = begin_event(idx, 1, s, &ev);
+        CK(idx, launch_finalize(fl, s));
+        if (timed) end_event(idx, ev, s);
+        idx->prof.finalize_launches++;
+        idx->prof.kernel_launches++;
+        idx->prof.queries += batch;
+        if (idx->pending.size() > 4096) drain_events(idx);
+        return DAWN_OK;
+    }
     const bool gemm_ok = idx->size >= 1024 && batch >= 1;
     const bool use_gemm = gemm_ok && !scan_only && idx->force_path != 1 &&
                           (idx->force_path == 2 ||
@@ -317,6 +402,7 @@ int search_enqueue(dawn_index *idx, const float *d_queries, size_t batch, size_t
         fl.distances_out = d_dist_out;
         fl.counts_out = d_counts;
         fl.flags_out = d_flags;
+        fl.scalar = 0;
         fl.eps_q = eps_q;
         fl.overflow = overflow;
         EventPair evf;
@@ -385,6 +471,7 @@ int search_enqueue(dawn_index *idx, const float *d_queries, size_t batch, size_t
     fl.distances_out = d_dist_out;
     fl.counts_out = d_counts;
     fl.flags_out = d_flags;
+    fl.scalar = 0;
     fl.eps_q = nullptr;
     fl.overflow = nullptr;
     EventPair ev;
@@ -416,8 +503,8 @@ int dawn_index_create(const dawn_options *opts, dawn_index **out) {
         return fail(DAWN_ERR_INVALID, "dimensions must be %d (src/search/vector.rs:26), got %u",
                     DAWN_DIMENSIONS, o.dimensions);
     if (o.metric != DAWN_METRIC_IP) return fail(DAWN_ERR_INVALID, "only MetricKind::IP is supported");
-    if (o.scalar != DAWN_SCALAR_F16)
-        return fail(DAWN_ERR_INVALID, "only DAWN_SCALAR_F16 storage is built in this version");
+    if (o.scalar != DAWN_SCALAR_F16 && o.scalar != DAWN_SCALAR_I8)
+        return fail(DAWN_ERR_INVALID, "scalar must be DAWN_SCALAR_F16 or DAWN_SCALAR_I8, got %u", o.scalar);
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0) {
@@ -436,6 +523,7 @@ int dawn_index_create(const dawn_options *opts, dawn_index **out) {
     dawn_index *idx = new (std::nothrow) dawn_index();
     if (!idx) return fail(DAWN_ERR_INTERNAL, "out of host memory");
     idx->device = o.device;
+    idx->scalar = (int)o.scalar;
     idx->sm_count = prop.multiProcessorCount;
     int rc = DAWN_OK;
     do {
@@ -545,7 +633,8 @@ int dawn_index_add_synthetic(dawn_index *idx, uint64_t seed, uint64_t first_row,
     if (idx->size + n > idx->capacity)
         return fail(DAWN_ERR_CAPACITY, "add of %zu vectors exceeds capacity %zu (size %zu): reserve first", n,
                     idx->capacity, idx->size);
-    CK(idx, launch_synth_f16(idx->corpus + idx->size * kDim, seed, first_row, n, idx->stream));
+    if (idx->scalar == DAWN_SCALAR_I8) CK(idx, launch_synth_i8(arena_i8(idx), idx->size, seed, first_row, n, idx->stream));
+    else CK(idx, launch_synth_f16(idx->corpus + idx->size * kDim, seed, first_row, n, idx->stream));
     idx->prof.kernel_launches++;
     // labels = first_row + i + 1, written by a tiny host-free path: reuse the staging buffer
     size_t done = 0;
@@ -672,7 +761,8 @@ int dawn_index_get(dawn_index *idx, uint64_t label, float *vector384_out) {
     CK(idx, cudaMemcpyAsync(idx->h_counts, idx->d_counts, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CK(idx, cudaStreamSynchronize(s));
     if (idx->h_counts[0] == kNoRow) return fail(DAWN_ERR_INVALID, "label %llu not found", (unsigned long long)label);
-    CK(idx, launch_gather_f32(idx->corpus, idx->d_counts, 1, idx->d_queries, s));
+    if (idx->scalar == DAWN_SCALAR_I8) CK(idx, launch_gather_f32_i8(arena_i8(idx), idx->d_counts, 1, idx->d_queries, s));
+    else CK(idx, launch_gather_f32(idx->corpus, idx->d_counts, 1, idx->d_queries, s));
     idx->prof.kernel_launches++;
     CK(idx, cudaMemcpyAsync(idx->h_queries, idx->d_queries, kDim * sizeof(float), cudaMemcpyDeviceToHost, s));
     CK(idx, cudaStreamSynchronize(s));
@@ -700,7 +790,7 @@ int dawn_index_save(dawn_index *idx, const char *path) {
     SaveHeader h{};
     memcpy(h.magic, "DAWNB200", 8);
     h.version = 1;
-    h.scalar = DAWN_SCALAR_F16;
+    h.scalar = (uint32_t)idx->scalar;
     h.dims = kDim;
     h.size = idx->size;
     bool ok = fwrite(&h, sizeof h, 1, f) == 1;
@@ -718,7 +808,7 @@ int dawn_index_save(dawn_index *idx, const char *path) {
         return DAWN_OK;
     };
     rc = dump(idx->labels, idx->size * sizeof(uint64_t));
-    if (rc == DAWN_OK) rc = dump(idx->corpus, idx->size * kRowBytesF16);
+    if (rc == DAWN_OK) rc = dump(idx->corpus, arena_bytes(idx, idx->size));
     ok = (fclose(f) == 0) && ok;
     if (rc != DAWN_OK || !ok) {
         remove(tmp.c_str());
@@ -740,15 +830,15 @@ int dawn_index_load(dawn_index *idx, const char *path) {
     if (!f) return fail(DAWN_ERR_IO, "cannot open %s", path);
     SaveHeader h{};
     if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "DAWNB200", 8) != 0 || h.version != 1 ||
-        h.scalar != DAWN_SCALAR_F16 || h.dims != kDim) {
+        h.scalar != (uint32_t)idx->scalar || h.dims != kDim) {
         fclose(f);
-        return fail(DAWN_ERR_IO, "%s is not a libdawn_b200 fp16 index file", path);
+        return fail(DAWN_ERR_IO, "%s is not a libdawn_b200 index file with this index's storage type", path);
     }
     // validate the length before touching the index, so a failed load leaves it unchanged
     // (the reference falls back to a rebuild when load fails, search_provider.rs:115-116)
     fseek(f, 0, SEEK_END);
     long long flen = ftell(f);
-    long long want = (long long)sizeof h + (long long)h.size * (8 + kRowBytesF16);
+    long long want = (long long)sizeof h + (long long)h.size * 8 + (long long)arena_bytes(idx, h.size);
     if (flen != want) {
         fclose(f);
         return fail(DAWN_ERR_IO, "%s is truncated (%lld bytes, expected %lld)", path, flen, want);
@@ -776,7 +866,7 @@ int dawn_index_load(dawn_index *idx, const char *path) {
     idx->staged = 0;
     idx->size = 0;  // from here on the old contents are gone
     rc = slurp(idx->labels, h.size * sizeof(uint64_t));
-    if (rc == DAWN_OK) rc = slurp(idx->corpus, h.size * kRowBytesF16);
+    if (rc == DAWN_OK) rc = slurp(idx->corpus, arena_bytes(idx, h.size));
     fclose(f);
     if (rc != DAWN_OK) return rc;
     if (!ok) return fail(DAWN_ERR_IO, "read error on %s", path);

@@ -84,7 +84,7 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
                 const Cand *__restrict__ partials, int n_lists, int kp, int k, float eps,
                 uint64_t *__restrict__ labels_out, float *__restrict__ distances_out,
                 uint32_t *__restrict__ counts_out, uint32_t *__restrict__ flags_out,
-                const float *__restrict__ eps_q, const uint32_t *__restrict__ overflow) {
+                const float *__restrict__ eps_q, const uint32_t *__restrict__ overflow, int scalar) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FinSmem &sm = *reinterpret_cast<FinSmem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -120,18 +120,32 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
         mine = sm.s[tid];
         sm.scan_score[tid] = mine.row != kNoRow ? mine.score : __int_as_float(0x7f800000);
         if (mine.row != kNoRow) {
-            const uint4 *rp = reinterpret_cast<const uint4 *>(corpus + (size_t)mine.row * kDim);
             float acc = 0.0f;
+            if (scalar == 0) {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(corpus + (size_t)mine.row * kDim);
 #pragma unroll 4
-            for (int c = 0; c < kDim / 8; c++) {
-                const uint4 u = __ldg(rp + c);
-                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+                for (int c = 0; c < kDim / 8; c++) {
+                    const uint4 u = __ldg(rp + c);
+                    const __half2 *h = reinterpret_cast<const __half2 *>(&u);
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float2 x = __half22float2(h[j]);
-                    acc = __fadd_rn(acc, __fmul_rn(sm.q[c * 8 + 2 * j], x.x));
-                    acc = __fadd_rn(acc, __fmul_rn(sm.q[c * 8 + 2 * j + 1], x.y));
+                    for (int j = 0; j < 4; j++) {
+                        const float2 x = __half22float2(h[j]);
+                        acc = __fadd_rn(acc, __fmul_rn(sm.q[c * 8 + 2 * j], x.x));
+                        acc = __fadd_rn(acc, __fmul_rn(sm.q[c * 8 + 2 * j + 1], x.y));
+                    }
                 }
+            } else {
+                // int8 rows: score = scale * sum q[i]*f32(x[i]) (oracle/dawn_oracle.c:dawn_oracle_search_i8)
+                const uint8_t *arena = reinterpret_cast<const uint8_t *>(corpus);
+                const uint4 *rp = reinterpret_cast<const uint4 *>(arena + i8_row_offset(mine.row));
+#pragma unroll 2
+                for (int c = 0; c < kDim / 16; c++) {
+                    const uint4 u = __ldg(rp + c);
+                    const int8_t *b = reinterpret_cast<const int8_t *>(&u);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) acc = __fadd_rn(acc, __fmul_rn(sm.q[c * 16 + j], (float)b[j]));
+                }
+                acc = __fmul_rn(*reinterpret_cast<const float *>(arena + i8_scale_offset(mine.row)), acc);
             }
             mine.score = __fsub_rn(1.0f, acc);  // distance, vector.rs:133
         }
@@ -197,7 +211,7 @@ cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s) {
     }
     finalize_kernel<<<p.nq, p.n_lists == 1 ? kFinThreadsSingle : kFinThreads, smem, s>>>(p.corpus, p.queries, p.partials, p.n_lists,
                                                    p.kprime, p.k, p.eps, p.labels_out, p.distances_out,
-                                                   p.counts_out, p.flags_out, p.eps_q, p.overflow);
+                                                   p.counts_out, p.flags_out, p.eps_q, p.overflow, p.scalar);
     return cudaGetLastError();
 }
 

@@ -89,14 +89,15 @@ __device__ __forceinline__ void consumer_bar_sync() {
 }
 
 // ---- shared-memory layout -------------------------------------------------------------
-template <int QT>
+template <int QT, int STAGES = kStages, int STAGE_BYTES = kStageBytes, int BUFCAP = kBufCap>
 struct ScanSmem {
-    alignas(128) uint8_t ring[kStages][kStageBytes];
+    static constexpr int kBuf = BUFCAP;
+    alignas(128) uint8_t ring[STAGES][STAGE_BYTES];
     alignas(16) Cand list[QT][kMaxCand];
-    alignas(16) Cand buf[QT][kBufCap];
-    alignas(8) uint64_t full_bar[kStages];
-    alignas(8) uint64_t empty_bar[kStages];
-    StageMeta meta[kStages];
+    alignas(16) Cand buf[QT][BUFCAP];
+    alignas(8) uint64_t full_bar[STAGES];
+    alignas(8) uint64_t empty_bar[STAGES];
+    StageMeta meta[STAGES];
     uint32_t cnt[QT];
     uint32_t list_len[QT];
     float thr[QT];
@@ -107,11 +108,11 @@ struct ScanSmem {
 // Merge the append buffer into the sorted list, all 512 consumer threads, one query at a time.
 // Rank of an entry = number of entries that beat it; the list part is already sorted so only
 // the buffer needs counting.  Entries are unique under cand_better, so ranks are unique.
-template <int QT>
-__device__ __forceinline__ void prune(ScanSmem<QT> &sm, int kprime, int tid) {
+template <int QT, class Smem>
+__device__ __forceinline__ void prune(Smem &sm, int kprime, int tid) {
 #pragma unroll 1
     for (int q = 0; q < QT; q++) {
-        const int nb = min((int)((volatile uint32_t *)sm.cnt)[q], kBufCap);
+        const int nb = min((int)((volatile uint32_t *)sm.cnt)[q], Smem::kBuf);
         const int len = (int)((volatile uint32_t *)sm.list_len)[q];
         const int total = len + nb;
         const bool have = tid < total;
@@ -346,15 +347,324 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
     if (tid == 0 && sm.overflow) atomicOr(status, 1u);  // cannot happen (static_assert above)
 }
 
+
+// ======================================================================================
+// K4: int8-stored corpus (config C5: 500M x 384 i8, ~24 GB per GPU).
+//
+// Storage is blocked: 8 rows x 384 int8 followed by their 8 f32 scales (kI8BlockBytes = 3104), so
+// one TMA bulk copy brings rows AND scales, and a stage is released before any prune rendezvous
+// exactly as in the fp16 kernel (a warp never holds a ring slot while it waits for other warps).  Precedents in the reference: distance_i8
+// (src/search/vector.rs:157-163) and ScalarKind::F8 in examples_old/search_usearch.rs:38; the
+// scheme (per-row absmax/127 scale, round half away like vector.rs:30-32) is restated in
+// oracle/dawn_oracle.c:dawn_oracle_store_i8.
+//
+// Roofline: HBM, 388 algorithmic bytes per row per pass.  With half the bytes per row the
+// issue budget per row halves too, so the dot product is integer: the f32 query is split into
+// two int8 vectors, q ~= s1*hi + s2*lo (residual ~3e-6 per element), and each row costs six
+// dp4a per lane per query.  Integer sums are exact, the score s_row*(s1*HI + s2*LO) is a pure
+// function of (row, query), and eps_q = ||q - s1*hi - s2*lo|| (Cauchy-Schwarz) bounds its
+// distance from the oracle's f32 score, which finalize.cu recomputes exactly.
+constexpr int kI8StageBlocks = 2;               // two 8-row blocks per stage: one 6,208-byte bulk copy
+constexpr int kI8StageRows = kI8BlockRows * kI8StageBlocks;
+constexpr int kI8StageBytes = kI8BlockBytes * kI8StageBlocks;
+constexpr int kI8Stages = 32;                   // 32 x 6208 B = 194 KB ring
+constexpr int kI8ChunkStages = 16;              // 256 rows per claim
+constexpr int kI8SubRows = kI8BlockRows;        // rows reduced per butterfly
+constexpr int kI8BufCap = 384;                  // a warp appends <= 16 rows per query between prune checks
+static_assert(kHighWater + kConsumerWarps * kI8StageRows <= kI8BufCap, "append buffer can overflow");
+static_assert(kMaxCand + kI8BufCap <= kConsumerThreads, "prune handles one entry per thread");
+
+template <int QT>
+using ScanSmemI8 = ScanSmem<QT, kI8Stages, kI8StageBytes, kI8BufCap>;
+
+template <int QT>
+__global__ void __launch_bounds__(kScanThreads, 1)
+scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restrict__ labels, uint32_t n_rows,
+                    const I8Query *__restrict__ queries, int kprime, Cand *__restrict__ partials,
+                    uint32_t *__restrict__ chunk_counter, uint32_t *__restrict__ status) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    ScanSmemI8<QT> &sm = *reinterpret_cast<ScanSmemI8<QT> *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < kI8Stages; s++) {
+            mbar_init(&sm.full_bar[s], 1);
+            mbar_init(&sm.empty_bar[s], 1);
+        }
+        sm.done_warps = 0;
+        sm.overflow = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < QT) {
+        sm.cnt[tid] = 0;
+        sm.list_len[tid] = 0;
+        sm.thr[tid] = __int_as_float(0xff800000);
+    }
+    __syncthreads();
+
+    const uint32_t n_blocks = (n_rows + kI8StageRows - 1) / kI8StageRows;  // stage-sized groups of blocks
+    if (warp == kConsumerWarps) {
+        // ===================== producer: two 3,104-byte blocks (16 rows) per stage =====================
+        if (lane != 0) return;
+        uint32_t g = 0;
+        uint32_t next = atomicAdd(chunk_counter, 1u);
+        while (true) {
+            const uint32_t chunk = next;
+            const uint64_t blk0 = (uint64_t)chunk * kI8ChunkStages;
+            if (blk0 >= n_blocks) break;
+            next = atomicAdd(chunk_counter, 1u);
+            const uint32_t n_stage = min((uint32_t)kI8ChunkStages, n_blocks - (uint32_t)blk0);
+            for (uint32_t s = 0; s < n_stage; s++, g++) {
+                const uint32_t slot = g % kI8Stages;
+                mbar_wait(&sm.empty_bar[slot], ((g / kI8Stages) & 1u) ^ 1u);
+                const uint32_t blk = (uint32_t)blk0 + s;
+                const uint32_t rb = blk * kI8StageRows;
+                const uint32_t nr = min((uint32_t)kI8StageRows, n_rows - rb);
+                // copy only the 8-row blocks that exist (the arena is allocated in whole blocks)
+                const uint32_t bytes = ((nr + kI8BlockRows - 1) / kI8BlockRows) * kI8BlockBytes;
+                sm.meta[slot].row_base = rb;
+                sm.meta[slot].n_rows = nr;
+                mbar_arrive_expect_tx(&sm.full_bar[slot], bytes);
+                bulk_g2s(sm.ring[slot], corpus + (size_t)blk * kI8StageBytes, bytes, &sm.full_bar[slot]);
+            }
+        }
+        for (int w = 0; w < kConsumerWarps; w++, g++) {
+            const uint32_t slot = g % kI8Stages;
+            mbar_wait(&sm.empty_bar[slot], ((g / kI8Stages) & 1u) ^ 1u);
+            sm.meta[slot].row_base = 0;
+            sm.meta[slot].n_rows = 0;
+            mbar_arrive(&sm.full_bar[slot]);
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    constexpr int V = kI8SubRows * QT * 2;              // (row, query, hi|lo) sums per butterfly
+    constexpr int LOGV = (V == 16) ? 4 : 5;
+    constexpr int REP = 32 / V;
+    const int my_idx = lane >> (5 - LOGV);
+    const int my_part = my_idx & 1;                     // 0 = hi sum, 1 = lo sum
+    const int my_r = (my_idx >> 1) / QT;
+    const int my_q = (my_idx >> 1) % QT;
+    const bool is_rep = my_part == 0 && (lane & (REP - 1)) == 0;
+
+    // This lane's query bytes: columns [8l, 8l+8) and [256+4l, 256+4l+4), hi and lo parts.
+    int qh[QT][3], ql[QT][3];
+    float s1[QT], s2[QT];
+#pragma unroll
+    for (int q = 0; q < QT; q++) {
+        const I8Query &iq = queries[q];
+        const uint2 h = *reinterpret_cast<const uint2 *>(iq.hi + lane * 8);
+        const uint2 l = *reinterpret_cast<const uint2 *>(iq.lo + lane * 8);
+        qh[q][0] = (int)h.x; qh[q][1] = (int)h.y;
+        qh[q][2] = *reinterpret_cast<const int *>(iq.hi + 256 + lane * 4);
+        ql[q][0] = (int)l.x; ql[q][1] = (int)l.y;
+        ql[q][2] = *reinterpret_cast<const int *>(iq.lo + 256 + lane * 4);
+        s1[q] = iq.s1;
+        s2[q] = iq.s2;
+    }
+    float my_s1 = s1[0], my_s2 = s2[0];
+#pragma unroll
+    for (int q = 1; q < QT; q++)
+        if (my_q == q) { my_s1 = s1[q]; my_s2 = s2[q]; }
+    uint32_t qmask[QT];
+#pragma unroll
+    for (int q = 0; q < QT; q++) qmask[q] = __ballot_sync(0xffffffffu, my_q == q && is_rep);
+
+    float thr = __int_as_float(0xff800000);
+    uint32_t g = warp;
+    while (true) {
+        {   // join a prune if any query's buffer reached the high-water mark (no slot is held here)
+            uint32_t c = lane < QT ? ((volatile uint32_t *)sm.cnt)[lane] : 0u;
+            if (__any_sync(0xffffffffu, c >= (uint32_t)kHighWater)) {
+                consumer_bar_sync();
+                prune<QT>(sm, kprime, tid);
+                thr = ((volatile float *)sm.thr)[my_q];
+                continue;
+            }
+        }
+        const uint32_t slot = g % kI8Stages;
+        mbar_wait(&sm.full_bar[slot], (g / kI8Stages) & 1u);
+        const uint32_t row_base = sm.meta[slot].row_base;
+        const uint32_t n_stage_rows = sm.meta[slot].n_rows;
+        if (n_stage_rows == 0) break;
+        const uint8_t *ring_slot = sm.ring[slot];
+#pragma unroll 1
+        for (int sub = 0; sub < kI8StageBlocks; sub++) {
+            if ((uint32_t)(sub * kI8SubRows) >= n_stage_rows) {  // second block absent in a ragged last stage
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty_bar[slot]);
+                break;
+            }
+            const uint8_t *sp = ring_slot + sub * kI8BlockBytes;
+            int v[V];
+#pragma unroll
+            for (int r = 0; r < kI8SubRows; r++) {
+                const uint8_t *rp = sp + r * kDim;
+                const uint2 a = *reinterpret_cast<const uint2 *>(rp + lane * 8);
+                const int b = *reinterpret_cast<const int *>(rp + 256 + lane * 4);
+#pragma unroll
+                for (int q = 0; q < QT; q++) {
+                    v[(r * QT + q) * 2 + 0] = __dp4a(b, qh[q][2], __dp4a((int)a.y, qh[q][1], __dp4a((int)a.x, qh[q][0], 0)));
+                    v[(r * QT + q) * 2 + 1] = __dp4a(b, ql[q][2], __dp4a((int)a.y, ql[q][1], __dp4a((int)a.x, ql[q][0], 0)));
+                }
+            }
+            const float row_scale = *reinterpret_cast<const float *>(sp + kI8BlockRows * kDim + my_r * 4);
+            if (sub == kI8StageBlocks - 1) {  // the stage's last bytes are in registers: hand the slot back
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty_bar[slot]);
+            }
+#pragma unroll
+            for (int s = 0; s < LOGV; s++) {
+                const int off = 16 >> s;
+                const int half = V >> (s + 1);
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < half; i++) {
+                    const int keep = up ? v[i + half] : v[i];
+                    const int send = up ? v[i] : v[i + half];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+#pragma unroll
+            for (int off = 16 >> LOGV; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+            const int other = __shfl_xor_sync(0xffffffffu, v[0], REP);  // the lane holding the other part
+            const int hi = my_part == 0 ? v[0] : other;
+            const int lo = my_part == 0 ? other : v[0];
+            float acc = __fmul_rn(my_s1, (float)hi);
+            acc = __fmaf_rn(my_s2, (float)lo, acc);
+            const float score = __fmul_rn(row_scale, acc);
+
+            const uint32_t r_in_stage = sub * kI8SubRows + my_r;
+            const bool pass = is_rep && r_in_stage < n_stage_rows && score >= thr;
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (m != 0) {
+                const uint32_t row = row_base + r_in_stage;
+                Cand c;
+                c.score = score;
+                c.row = row;
+                c.label = 0;
+                if (pass) c.label = labels ? labels[row] : (uint64_t)row + 1;
+#pragma unroll
+                for (int q = 0; q < QT; q++) {
+                    const uint32_t mq = m & qmask[q];
+                    if (mq == 0) continue;
+                    const int leader = __ffs(mq) - 1;
+                    uint32_t base = 0;
+                    if (lane == leader) base = atomicAdd(&sm.cnt[q], (uint32_t)__popc(mq));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (pass && my_q == q) {
+                        const uint32_t pos = base + __popc(mq & ((1u << lane) - 1u));
+                        if (pos < (uint32_t)kI8BufCap) sm.buf[q][pos] = c;
+                        else sm.overflow = 1;
+                    }
+                }
+            }
+        }
+        g += kConsumerWarps;
+    }
+
+    __syncwarp();
+    if (lane == 0) atomicAdd(&sm.done_warps, 1u);
+    while (true) {
+        consumer_bar_sync();
+        const uint32_t done = *((volatile uint32_t *)&sm.done_warps);
+        prune<QT>(sm, kprime, tid);
+        if (done == (uint32_t)kConsumerWarps) break;
+    }
+    for (int i = tid; i < QT * kprime; i += kConsumerThreads) {
+        const int q = i / kprime, j = i % kprime;
+        Cand c = j < (int)sm.list_len[q] ? sm.list[q][j] : empty_cand();
+        partials[((size_t)q * gridDim.x + blockIdx.x) * kprime + j] = c;
+    }
+    if (tid == 0 && sm.overflow) atomicOr(status, 1u);
+}
+
+// f32 query -> two int8 vectors + scales + eps (one 128-thread block per query).
+__global__ void __launch_bounds__(128) prep_queries_i8_kernel(const float *__restrict__ q32, int n_queries,
+                                                              I8Query *__restrict__ out, float *__restrict__ eps_q) {
+    const int qi = blockIdx.x;
+    if (qi >= n_queries) return;
+    __shared__ float red[4];
+    const float *q = q32 + (size_t)qi * kDim;
+    auto block_max = [&](float x) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, off));
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+        __syncthreads();
+        return fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    };
+    float x[3], amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        x[j] = q[threadIdx.x + 128 * j];
+        amax = fmaxf(amax, fabsf(x[j]));
+    }
+    amax = block_max(amax);
+    const float s1 = amax > 0.f ? amax / 127.0f : 1.0f;
+    float r[3], rmax = 0.f;
+    int hi[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        hi[j] = max(-127, min(127, (int)rintf(x[j] / s1)));
+        r[j] = fmaf(-s1, (float)hi[j], x[j]);
+        rmax = fmaxf(rmax, fabsf(r[j]));
+    }
+    rmax = block_max(rmax);
+    const float s2 = rmax > 0.f ? rmax / 127.0f : 1.0f;
+    float err2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int lo = max(-127, min(127, (int)rintf(r[j] / s2)));
+        const float e = fmaf(-s2, (float)lo, r[j]);
+        err2 += e * e;
+        out[qi].hi[threadIdx.x + 128 * j] = (int8_t)hi[j];
+        out[qi].lo[threadIdx.x + 128 * j] = (int8_t)lo;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = err2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out[qi].s1 = s1;
+        out[qi].s2 = s2;
+        // |sum e_i x_i| <= ||e|| * ||x||; dequantised rows have norm < 1.02; + f32 rounding of the
+        // three-operation score formula
+        eps_q[qi] = sqrtf(red[0] + red[1] + red[2] + red[3]) * 1.03f + 2.0e-5f;
+    }
+}
+
+template <int QT>
+cudaError_t launch_i8_qt(const ScanLaunchI8 &p, cudaStream_t s) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem = sizeof(ScanSmemI8<QT>);
+    if (dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(scan_topk_i8_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    scan_topk_i8_kernel<QT><<<p.grid, kScanThreads, smem, s>>>(p.corpus, p.labels, p.n_rows, p.queries, p.kprime,
+                                                              p.partials, p.chunk_counter, p.status);
+    return cudaGetLastError();
+}
+
 template <int QT>
 cudaError_t launch_qt(const ScanLaunch &p, cudaStream_t s) {
-    static bool configured = false;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
     const size_t smem = sizeof(ScanSmem<QT>);
-    if (!configured) {
+    if (dev < 64 && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(scan_topk_f16_kernel<QT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     scan_topk_f16_kernel<QT><<<p.grid, kScanThreads, smem, s>>>(
         p.corpus, p.labels, p.n_rows, p.queries, p.kprime, p.partials, p.chunk_counter, p.status);
@@ -371,6 +681,21 @@ cudaError_t launch_scan_topk_f16(const ScanLaunch &p, cudaStream_t s) {
         case 1: return launch_qt<1>(p, s);
         case 2: return launch_qt<2>(p, s);
         case 4: return launch_qt<4>(p, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_prep_queries_i8(const float *q32, int n_queries, I8Query *out, float *eps_q, cudaStream_t s) {
+    if (n_queries <= 0) return cudaSuccess;
+    prep_queries_i8_kernel<<<n_queries, 128, 0, s>>>(q32, n_queries, out, eps_q);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_topk_i8(const ScanLaunchI8 &p, cudaStream_t s) {
+    if (p.kprime < 1 || p.kprime > kMaxCand) return cudaErrorInvalidValue;
+    switch (p.nq) {
+        case 1: return launch_i8_qt<1>(p, s);
+        case 2: return launch_i8_qt<2>(p, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -152,8 +152,8 @@ class Index:
 
     def __init__(self, options: IndexOptions):
         L = load_library()
-        if options.quantization not in (ScalarKind.F16,):
-            raise DawnError(-1, "only ScalarKind.F16 storage is built in this version")
+        if options.quantization not in (ScalarKind.F16, ScalarKind.I8):
+            raise DawnError(-1, "quantization must be ScalarKind.F16 or ScalarKind.I8")
         o = _Options(options.dimensions, options.metric, options.quantization, options.device,
                      options.capacity, 0, 0)
         h = _vp()

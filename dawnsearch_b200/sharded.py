@@ -56,13 +56,13 @@ def all_gather_blocks(local: torch.Tensor, gathered: torch.Tensor, group=None):
 class ShardedIndex:
     """One rank's shard plus the collective search.  All ranks must call `search*` together."""
 
-    def __init__(self, device: int, capacity: int, group=None):
+    def __init__(self, device: int, capacity: int, group=None, quantization: int = 0):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.device = device
         self.tdev = torch.device("cuda", device)
-        self.index: Index = new_index(IndexOptions(device=device, capacity=capacity))
+        self.index: Index = new_index(IndexOptions(device=device, capacity=capacity, quantization=quantization))
         self._ws = {}
 
     def close(self):

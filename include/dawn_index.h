@@ -65,7 +65,7 @@ enum { DAWN_METRIC_IP = 0 };
 typedef struct dawn_options {
     uint32_t dimensions; /* must be 384 (0 = default) */
     uint32_t metric;     /* DAWN_METRIC_IP */
-    uint32_t scalar;     /* DAWN_SCALAR_F16 (DAWN_SCALAR_I8: not in this build) */
+    uint32_t scalar;     /* DAWN_SCALAR_F16, or DAWN_SCALAR_I8 (per-vector absmax/127 scale, 388 B per vector) */
     int32_t device;      /* CUDA device ordinal */
     uint64_t capacity;   /* vectors to reserve up front (0 = none) */
     uint32_t flags;      /* reserved, 0 */

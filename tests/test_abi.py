@@ -61,7 +61,7 @@ def test_argument_validation_needs_no_gpu(dawn):
     opts = dawn.index._Options(128, 0, 0, 0, 0, 0, 0)  # wrong dimension
     assert lib.dawn_index_create(C.byref(opts), C.byref(h)) == -1
     assert b"384" in lib.dawn_last_error()
-    opts = dawn.index._Options(384, 0, 1, 0, 0, 0, 0)  # i8 storage is not in this build
+    opts = dawn.index._Options(384, 0, 7, 0, 0, 0, 0)  # unknown storage kind
     assert lib.dawn_index_create(C.byref(opts), C.byref(h)) == -1
     assert lib.dawn_index_size(None) == 0
     assert lib.dawn_index_reserve(None, 10) == -1
