@@ -134,6 +134,24 @@ def load_library() -> C.CDLL:
     L.dawn_index_set_profiling.argtypes = [_vp, C.c_int]
     L.dawn_index_set_option.argtypes = [_vp, C.c_char_p, C.c_int64]
     L.dawn_index_get_profile.argtypes = [_vp, C.POINTER(Profile), C.c_int]
+    L.dawn_vector_length.argtypes = [_vp]
+    L.dawn_vector_length.restype = C.c_float
+    L.dawn_is_normalized.argtypes = [_vp]
+    L.dawn_normalize.argtypes = [_vp]
+    L.dawn_normalize.restype = None
+    L.dawn_encode_i24.argtypes = [_vp, _vp]
+    L.dawn_encode_i24.restype = None
+    L.dawn_decode_i24.argtypes = [_vp, _vp]
+    L.dawn_index_search_limit.argtypes = [_vp, _vp, C.c_size_t, C.c_float, _vp, _vp, _vp]
+    L.dawn_index_search_i24.argtypes = [_vp, _vp, C.c_size_t, C.c_int, C.c_float, _vp, _vp, _vp]
+    L.dawn_index_get_i24.argtypes = [_vp, C.c_uint64, _vp]
+    L.dawn_index_add_page_entries.argtypes = [_vp, _vp, C.c_size_t, C.c_uint64, _vp]
+    L.dawn_batcher_create.argtypes = [_vp, C.c_size_t, C.c_uint32, C.POINTER(_vp)]
+    L.dawn_batcher_search.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp, _vp]
+    L.dawn_batcher_stats.argtypes = [_vp, _vp, _vp, _vp]
+    L.dawn_batcher_last_error.restype = C.c_char_p
+    L.dawn_batcher_free.argtypes = [_vp]
+    L.dawn_batcher_free.restype = None
     _lib = L
     return L
 
@@ -241,6 +259,41 @@ class Index:
         _check(self._L.dawn_index_get(self._h, int(label), _ptr(out)))
         return out
 
+    def search_limit(self, query, count: int, distance_limit: float) -> Matches:
+        """Hits with distance >= distance_limit are dropped (src/net/udp_service.rs:196-199)."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        labels = np.zeros(max(count, 1), dtype=np.uint64)
+        dist = np.zeros(max(count, 1), dtype=np.float32)
+        n = C.c_size_t(0)
+        _check(self._L.dawn_index_search_limit(self._h, _ptr(q), count, distance_limit, _ptr(labels), _ptr(dist),
+                                               C.byref(n)))
+        return Matches(labels[: n.value].copy(), dist[: n.value].copy())
+
+    def search_i24(self, query1152: bytes, count: int, distance_limit=None) -> Matches:
+        """The peer side of UdpPacket::Search: raw i24 query bytes, optional distance_limit."""
+        buf = np.frombuffer(query1152, dtype=np.uint8).copy()
+        labels = np.zeros(max(count, 1), dtype=np.uint64)
+        dist = np.zeros(max(count, 1), dtype=np.float32)
+        n = C.c_size_t(0)
+        _check(self._L.dawn_index_search_i24(self._h, _ptr(buf), count, int(distance_limit is not None),
+                                             float(distance_limit or 0.0), _ptr(labels), _ptr(dist), C.byref(n)))
+        return Matches(labels[: n.value].copy(), dist[: n.value].copy())
+
+    def get_i24(self, label: int) -> bytes:
+        out = np.zeros(EM_LEN * 3, dtype=np.uint8)
+        _check(self._L.dawn_index_get_i24(self._h, int(label), _ptr(out)))
+        return out.tobytes()
+
+    def add_page_entries(self, entries: bytes, first_label: int) -> int:
+        """Bulk load of a legacy `.emb` file (1568-byte PageEntry records); returns #skipped."""
+        buf = np.frombuffer(entries, dtype=np.uint8)
+        if buf.shape[0] % 1568:
+            raise DawnError(-1, "a .emb file is a whole number of 1568-byte PageEntry records")
+        skipped = C.c_size_t(0)
+        _check(self._L.dawn_index_add_page_entries(self._h, _ptr(buf), buf.shape[0] // 1568, first_label,
+                                                   C.byref(skipped)))
+        return int(skipped.value)
+
     def add_synthetic(self, seed: int, first_row: int, n: int) -> None:
         _check(self._L.dawn_index_add_synthetic(self._h, seed, first_row, n))
 
@@ -261,6 +314,74 @@ class Index:
         p = Profile()
         _check(self._L.dawn_index_get_profile(self._h, C.byref(p), int(reset)))
         return p.as_dict()
+
+
+# ---- host mirrors of src/search/vector.rs (no GPU needed) ---------------------------------------
+
+
+def is_normalized(v) -> bool:  # vector.rs:185-192
+    a = np.ascontiguousarray(v, dtype=np.float32)
+    return bool(load_library().dawn_is_normalized(_ptr(a)))
+
+
+def normalize(v) -> np.ndarray:  # vector.rs:194-197
+    a = np.ascontiguousarray(v, dtype=np.float32).copy()
+    load_library().dawn_normalize(_ptr(a))
+    return a
+
+
+def encode_i24(v) -> bytes:  # vector.rs:74-86 (to24)
+    a = np.ascontiguousarray(v, dtype=np.float32)
+    out = np.zeros(EM_LEN * 3, dtype=np.uint8)
+    load_library().dawn_encode_i24(_ptr(a), _ptr(out))
+    return out.tobytes()
+
+
+def decode_i24(data: bytes) -> np.ndarray:  # vector.rs:52-72 (from24); raises if not normalised
+    buf = np.frombuffer(data, dtype=np.uint8).copy()
+    if buf.shape[0] != EM_LEN * 3:
+        raise DawnError(-1, "an i24 embedding is 1152 bytes")
+    out = np.zeros(EM_LEN, dtype=np.float32)
+    if load_library().dawn_decode_i24(_ptr(buf), _ptr(out)) != 0:
+        raise DawnError(-1, "Embedding is not normalized")
+    return out
+
+
+class Batcher:
+    """Micro-batching front: `search` may be called from many threads at once."""
+
+    def __init__(self, index: "Index", max_batch: int = 256, max_wait_us: int = 200):
+        self._L = load_library()
+        h = _vp()
+        _check(self._L.dawn_batcher_create(index._h, max_batch, max_wait_us, C.byref(h)))
+        self._h = h
+        self._index = index  # keep the index alive
+
+    def search(self, query, count: int) -> Matches:
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        labels = np.zeros(max(count, 1), dtype=np.uint64)
+        dist = np.zeros(max(count, 1), dtype=np.float32)
+        n = C.c_size_t(0)
+        rc = self._L.dawn_batcher_search(self._h, _ptr(q), count, _ptr(labels), _ptr(dist), C.byref(n))
+        if rc != 0:
+            raise DawnError(rc, self._L.dawn_batcher_last_error().decode("utf-8", "replace"))
+        return Matches(labels[: n.value].copy(), dist[: n.value].copy())
+
+    def stats(self) -> dict:
+        b, q, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self._L.dawn_batcher_stats(self._h, C.byref(b), C.byref(q), C.byref(m)))
+        return {"batches": b.value, "queries": q.value, "largest_batch": m.value}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dawn_batcher_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def new_index(options: IndexOptions | None = None) -> Index:

@@ -134,6 +134,47 @@ int dawn_merge_results_device(int device, const uint64_t *d_labels, const float 
  * a test budget.  Bit-identical to oracle/dawn_oracle.c:dawn_oracle_synth_rows_f16. */
 int dawn_index_add_synthetic(dawn_index *idx, uint64_t seed, uint64_t first_row, size_t n);
 
+/* ---- callers and formats either side of the path ------------------------- */
+
+/* Host mirrors of the reference's normalisation gate and helpers (src/search/vector.rs:181-197),
+ * same sequential f32 arithmetic. */
+float dawn_vector_length(const float *v384);
+int dawn_is_normalized(const float *v384); /* 1 if finite and 0.99 < |v| < 1.01 */
+void dawn_normalize(float *v384);
+/* The i24 wire codec of query embeddings (src/search/vector.rs:48-87; UdpPacket::Search carries
+ * 1152 bytes, src/net/udp_packets.rs:35-38).  decode returns DAWN_ERR_INVALID when the decoded
+ * vector is not normalised, like the reference's ensure!(). */
+void dawn_encode_i24(const float *v384, uint8_t *out1152);
+int dawn_decode_i24(const uint8_t *in1152, float *out384);
+
+/* distance_limit of UdpPacket::Search: hits with distance >= limit are not returned
+ * (src/net/udp_service.rs:196-199).  NaN limit = no limit. */
+int dawn_index_search_limit(dawn_index *idx, const float *query384, size_t k, float distance_limit,
+                            uint64_t *labels_out, float *distances_out, size_t *count_out);
+/* The peer side of a remote search: raw i24 query in (udp_service.rs:174-213). */
+int dawn_index_search_i24(dawn_index *idx, const uint8_t *query1152, size_t k, int has_limit, float distance_limit,
+                          uint64_t *labels_out, float *distances_out, size_t *count_out);
+/* Stored vector in wire format (GetEmbedding over UDP, udp_service.rs:254-276). */
+int dawn_index_get_i24(dawn_index *idx, uint64_t label, uint8_t *out1152);
+
+/* Bulk load of a legacy `.emb` flat file: n repr(C) PageEntry records of 1568 bytes (url_pos u64,
+ * title_pos u64, vector [f32;384], url_len u64, title_len u64; src/index/warc.rs:35-43), labels
+ * first_label + i.  Records failing the normalisation gate are skipped and counted. */
+int dawn_index_add_page_entries(dawn_index *idx, const void *entries, size_t n, uint64_t first_label,
+                                size_t *skipped);
+
+/* Micro-batching front.  The reference answers one query at a time from one thread
+ * (src/search/search_service.rs:55-104); a batcher lets any number of threads call
+ * dawn_batcher_search concurrently and answers them in batches of up to max_batch queries,
+ * waiting at most max_wait_us for a batch to fill.  Results equal dawn_index_search's. */
+typedef struct dawn_batcher dawn_batcher;
+int dawn_batcher_create(dawn_index *idx, size_t max_batch, uint32_t max_wait_us, dawn_batcher **out);
+int dawn_batcher_search(dawn_batcher *b, const float *query384, size_t k, uint64_t *labels_out,
+                        float *distances_out, size_t *count_out);
+int dawn_batcher_stats(dawn_batcher *b, uint64_t *batches, uint64_t *queries, uint64_t *largest_batch);
+const char *dawn_batcher_last_error(void);
+void dawn_batcher_free(dawn_batcher *b);
+
 /* ---- instrumentation ------------------------------------------------------------------- */
 typedef struct dawn_profile {
     uint64_t scan_launches;  /* K2 launches since the last reset */

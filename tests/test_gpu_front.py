@@ -1,0 +1,98 @@
+"""GPU tests of the callers / formats either side of the hot path:
+micro-batching front, distance_limit, i24 wire queries, legacy .emb bulk load."""
+import struct
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+SEED = 0xDA5EA2C4
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def small(dawn, oracle):
+    n = 20000
+    rows = oracle.np_synth_rows_f32(SEED, 0, n)
+    idx = dawn.new_index(dawn.IndexOptions(capacity=n))
+    idx.add_batch(np.arange(1, n + 1, dtype=np.uint64), rows)
+    yield idx, rows, oracle.store_f16(rows)
+    idx.close()
+
+
+def test_batcher_coalesces_concurrent_callers(dawn, oracle, small):
+    """32 threads x 8 single-query searches (the reference's calling pattern, one query per
+    message: search_service.rs:55-104) are answered in batches and equal the oracle."""
+    idx, rows, stored = small
+    qs = oracle.make_queries(SEED, 77, 256, len(rows))
+    want = [oracle.search_f16(stored, None, q, 20) for q in qs]
+    b = dawn.Batcher(idx, max_batch=64, max_wait_us=2000)
+    got = [None] * len(qs)
+
+    def worker(t):
+        for i in range(t, len(qs), 32):
+            got[i] = b.search(qs[i], 20)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(32)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for m, (wl, wd) in zip(got, want):
+        assert (m.labels == wl).all() and (bits(m.distances) == bits(wd)).all()
+    st = b.stats()
+    assert st["queries"] == 256 and st["batches"] < 256 and st["largest_batch"] > 1
+    b.close()
+
+
+def test_distance_limit_drops_far_hits(small, oracle):
+    idx, rows, stored = small
+    q = oracle.make_queries(SEED, 5, 1, len(rows))[0]
+    full = idx.search(q, 20)
+    limit = float(full.distances[7])  # udp_service.rs:196-199: distance >= limit is dropped
+    m = idx.search_limit(q, 20, limit)
+    assert len(m.labels) == int((full.distances < limit).sum()) <= 7
+    assert (m.labels == full.labels[: len(m.labels)]).all()
+    assert len(idx.search_limit(q, 20, float("inf")).labels) == 20
+    assert len(idx.search_limit(q, 20, -1.0).labels) == 0
+
+
+def test_i24_wire_query_and_stored_vector(dawn, small, oracle):
+    idx, rows, stored = small
+    q = oracle.make_queries(SEED, 6, 1, len(rows))[0]
+    wire = dawn.encode_i24(q)
+    assert len(wire) == 1152
+    decoded = dawn.decode_i24(wire)
+    m = idx.search_i24(wire, 20)
+    wl, wd = oracle.search_f16(stored, None, decoded, 20)  # the peer searches with the DECODED query
+    assert (m.labels == wl).all() and (bits(m.distances) == bits(wd)).all()
+    lim = float(wd[5])
+    assert len(idx.search_i24(wire, 20, lim).labels) == int((wd < lim).sum())
+    sv = idx.get_i24(17)
+    assert sv == oracle.to24(stored[16].astype(np.float32))
+    with pytest.raises(dawn.DawnError):
+        idx.search_i24(bytes(1152), 20)  # decodes to all -1: not normalised
+
+
+def test_legacy_emb_bulk_load(dawn, oracle):
+    """`.emb` files are arrays of repr(C) PageEntry (src/index/warc.rs:35-43)."""
+    n = 3000
+    rows = oracle.np_synth_rows_f32(31, 0, n)
+    rows[10] *= 3.0  # a record that fails the normalisation gate is skipped
+    blob = b"".join(struct.pack("<QQ", i * 7, i * 11) + rows[i].tobytes() + struct.pack("<QQ", 20, 30) for i in range(n))
+    assert len(blob) == n * 1568
+    with dawn.new_index(dawn.IndexOptions(capacity=n)) as idx:
+        skipped = idx.add_page_entries(blob, first_label=1)
+        assert skipped == 1 and idx.size() == n - 1
+        keep = np.ones(n, dtype=bool)
+        keep[10] = False
+        stored = oracle.store_f16(rows[keep])
+        labels = (np.arange(n, dtype=np.uint64) + 1)[keep]
+        q = oracle.make_queries(31, 32, 1, n)[0]
+        m = idx.search(q, 20)
+        wl, wd = oracle.search_f16(stored, labels, q, 20)
+        assert (m.labels == wl).all() and (bits(m.distances) == bits(wd)).all()

@@ -111,3 +111,29 @@ def test_sharded_exchange_world2_gloo(rows, k):
         p.join(120)
         assert p.exitcode == 0
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+# ---- host mirrors of src/search/vector.rs inside libdawn_b200 (no GPU needed) -------------------
+
+
+def test_library_vector_helpers_match_oracle(dawn, oracle):
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        v = rng.standard_normal(384).astype(np.float32)
+        assert (dawn.normalize(v).view(np.uint32) == oracle.normalize(v).view(np.uint32)).all()
+        u = dawn.normalize(v)
+        assert dawn.is_normalized(u) and oracle.is_normalized(u)
+        for scale in (0.9899, 0.99, 0.9901, 1.0099, 1.01, 1.0101):
+            w = (u * np.float32(scale)).astype(np.float32)
+            assert dawn.is_normalized(w) == oracle.is_normalized(w)
+        data = dawn.encode_i24(u)
+        assert data == oracle.to24(u)  # vector.rs:74-86
+        back = dawn.decode_i24(data)
+        ob, ok = oracle.from24(data)
+        assert ok and (back.view(np.uint32) == ob.view(np.uint32)).all()  # vector.rs:52-72
+    bad = np.zeros(384, dtype=np.float32)
+    assert not dawn.is_normalized(bad)
+    with pytest.raises(dawn.DawnError):
+        dawn.decode_i24(dawn.encode_i24(bad))  # "Embedding is not normalized"
+    nan = np.full(384, np.nan, dtype=np.float32)
+    assert not dawn.is_normalized(nan)
