@@ -47,11 +47,20 @@ def parse():
     ap.add_argument("--batch", type=int, default=1024, help="queries per step")
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--scalar", default="f16", choices=["f16", "i8"], help="stored precision of the corpus")
-    ap.add_argument("--latency-steps", type=int, default=30, help="batch-1 steps for the latency section (0 = skip)")
+    ap.add_argument("--latency-steps", type=int, default=200, help="batch-1 steps for the latency section (0 = skip)")
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", default="", help="extra device-resident points: 'batch[:k],...' e.g. 1,4,16:100")
     return ap.parse_args()
+
+
+def ncu_traffic_ratio(kernel_key: str):
+    """DRAM bytes / algorithmic bytes of a kernel from the committed ncu captures (profiles/ncu_summary.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            return float(json.load(f)[kernel_key]["traffic_over_algorithmic"])
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -264,9 +273,13 @@ def run_ours(args):
             gms = prof["gemm_ms"] / int(prof["gemm_batches"])
             flops = 2.0 * batch * n_local * DIM
             ach = flops / (gms / 1e3) / 1e12
+            ratio = ncu_traffic_ratio("gemm_topk_kernel<2> final round")
             return {"bound": "tensor", "kernel": "gemm_topk_kernel (tcgen05; all rounds of a batch incl. select)",
                     "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["tf_sustained"], "traffic": None,
+                    "frac": ach / peaks["tf_sustained"],
+                    "traffic": ratio * n_local * row_bytes if ratio else None,
+                    "traffic_note": "DRAM bytes per batch = ncu dram bytes / corpus bytes of the captured round "
+                                    "(profiles/ncu_summary.json) x this shard's corpus bytes",
                     "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "frac_of_burst_peak": ach / peaks["tf_burst"], "frac_of_nominal_2250": ach / 2250.0,
                     "algorithmic_flops_per_batch": flops, "avg_batch_ms": gms,
@@ -275,8 +288,10 @@ def run_ours(args):
         sms = prof["scan_ms"] / launches
         algo = n_local * row_bytes
         ach = algo / (sms / 1e3) / 1e9 if sms > 0 else 0.0
+        ratio = ncu_traffic_ratio("scan_topk_f16_kernel<1>" if args.scalar == "f16" else "scan_topk_i8_kernel<1>")
         return {"bound": "hbm", "kernel": "scan_topk_f16_kernel" if args.scalar == "f16" else "scan_topk_i8_kernel", "achieved": ach, "peak": peaks["hbm"],
-                "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
+                "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": ratio * algo if ratio else None,
+                "traffic_note": "ncu dram bytes / algorithmic bytes of the captured launch (profiles/ncu_summary.json) x this launch's algorithmic bytes",
                 "peak_source": peaks["source"] + " hbm_gbs", "frac_of_nominal_8TBs": ach / 8000.0,
                 "algorithmic_bytes_per_launch": algo, "avg_launch_ms": sms, "launches_timed": int(prof["scan_launches"])}
 
@@ -300,8 +315,8 @@ def run_ours(args):
     if args.latency_steps > 0 and B != 1:
         q1_host = [pool_host[0][i:i + 1] for i in range(min(B, 16))]
         q1_dev = [pool_dev[0][i:i + 1] for i in range(min(B, 16))]
-        t_ms, s_ms, p1, _ = timed_device(q1_dev, k, args.latency_steps, 3)
-        e_s, l1 = timed_e2e(q1_host, k, args.latency_steps, 3)
+        t_ms, s_ms, p1, _ = timed_device(q1_dev, k, args.latency_steps, 20)
+        e_s, l1 = timed_e2e(q1_host, k, args.latency_steps, 20)
         l1s = sorted(l1)
         batch1 = {"qps_device": args.latency_steps / (t_ms / 1e3), "qps_e2e": args.latency_steps / e_s,
                   "latency_ms": {"device_p50": statistics.median(s_ms), "device_max": max(s_ms),

@@ -64,6 +64,14 @@ struct dawn_index {
     size_t phys = 0;      // rows actually allocated
 
     // staged adds (host, pinned) not yet on the device
+    // Two buffers: while the GPU copies / converts one, the host fills the other (pipelined
+    // bulk load).  h_stage / h_stage_labels / d_stage alias the buffer being filled.
+    float *h_stage_buf[2] = {nullptr, nullptr};
+    uint64_t *h_labels_buf[2] = {nullptr, nullptr};
+    float *d_stage_buf[2] = {nullptr, nullptr};
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    bool stage_busy[2] = {false, false};
+    int stage_cur = 0;
     float *h_stage = nullptr;
     uint64_t *h_stage_labels = nullptr;
     size_t staged = 0;
@@ -201,18 +209,40 @@ int grow_physical(dawn_index *idx, size_t rows) {
     return DAWN_OK;
 }
 
-// Move staged host vectors to the device corpus: H2D of the f32 rows, K1 convert, labels.
-int flush_staged(dawn_index *idx) {
+// Enqueue the current staging buffer (H2D of the f32 rows, K1 convert, labels) WITHOUT waiting, and
+// switch to the other buffer (waiting only if that one is still in flight).
+int flush_staged_async(dawn_index *idx) {
     if (idx->staged == 0) return DAWN_OK;
     const size_t n = idx->staged;
+    const int cur = idx->stage_cur;
     CK(idx, cudaMemcpyAsync(idx->d_stage, idx->h_stage, n * kDim * sizeof(float), cudaMemcpyHostToDevice, idx->stream));
     if (idx->scalar == DAWN_SCALAR_I8) CK(idx, launch_ingest_i8(idx->d_stage, arena_i8(idx), idx->size, n, idx->stream));
     else CK(idx, launch_ingest_f16(idx->d_stage, idx->corpus + idx->size * kDim, n, idx->stream));
     idx->prof.kernel_launches++;
     CK(idx, cudaMemcpyAsync(idx->labels + idx->size, idx->h_stage_labels, n * sizeof(uint64_t), cudaMemcpyHostToDevice, idx->stream));
-    CK(idx, cudaStreamSynchronize(idx->stream));
+    CK(idx, cudaEventRecord(idx->stage_done[cur], idx->stream));
+    idx->stage_busy[cur] = true;
     idx->size += n;
     idx->staged = 0;
+    const int nxt = cur ^ 1;
+    if (idx->stage_busy[nxt]) {
+        CK(idx, cudaEventSynchronize(idx->stage_done[nxt]));
+        idx->stage_busy[nxt] = false;
+    }
+    idx->stage_cur = nxt;
+    idx->h_stage = idx->h_stage_buf[nxt];
+    idx->h_stage_labels = idx->h_labels_buf[nxt];
+    idx->d_stage = idx->d_stage_buf[nxt];
+    return DAWN_OK;
+}
+
+// Make every staged / in-flight add visible: flush what is staged and wait for the stream.
+int flush_staged(dawn_index *idx) {
+    if (idx->staged == 0 && !idx->stage_busy[0] && !idx->stage_busy[1]) return DAWN_OK;
+    int rc = flush_staged_async(idx);
+    if (rc) return rc;
+    CK(idx, cudaStreamSynchronize(idx->stream));
+    idx->stage_busy[0] = idx->stage_busy[1] = false;
     return DAWN_OK;
 }
 
@@ -529,9 +559,16 @@ int dawn_index_create(const dawn_options *opts, dawn_index **out) {
     do {
         if ((e = cudaSetDevice(o.device)) != cudaSuccess) break;
         if ((e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking)) != cudaSuccess) break;
-        if ((e = cudaMallocHost(&idx->h_stage, kStageRowsHost * kDim * sizeof(float))) != cudaSuccess) break;
-        if ((e = cudaMallocHost(&idx->h_stage_labels, kStageRowsHost * sizeof(uint64_t))) != cudaSuccess) break;
-        if ((e = cudaMalloc(&idx->d_stage, kStageRowsHost * kDim * sizeof(float))) != cudaSuccess) break;
+        for (int b = 0; b < 2 && e == cudaSuccess; b++) {
+            if ((e = cudaMallocHost(&idx->h_stage_buf[b], kStageRowsHost * kDim * sizeof(float))) != cudaSuccess) break;
+            if ((e = cudaMallocHost(&idx->h_labels_buf[b], kStageRowsHost * sizeof(uint64_t))) != cudaSuccess) break;
+            if ((e = cudaMalloc(&idx->d_stage_buf[b], kStageRowsHost * kDim * sizeof(float))) != cudaSuccess) break;
+            if ((e = cudaEventCreateWithFlags(&idx->stage_done[b], cudaEventDisableTiming)) != cudaSuccess) break;
+        }
+        if (e != cudaSuccess) break;
+        idx->h_stage = idx->h_stage_buf[0];
+        idx->h_stage_labels = idx->h_labels_buf[0];
+        idx->d_stage = idx->d_stage_buf[0];
         if ((e = cudaMallocHost(&idx->h_word, 64)) != cudaSuccess) break;
     } while (0);
     if (e != cudaSuccess) {
@@ -562,9 +599,12 @@ void dawn_index_free(dawn_index *idx) {
     }
     cudaFree(idx->corpus);
     cudaFree(idx->labels);
-    cudaFree(idx->d_stage);
-    cudaFreeHost(idx->h_stage);
-    cudaFreeHost(idx->h_stage_labels);
+    for (int b = 0; b < 2; b++) {
+        cudaFree(idx->d_stage_buf[b]);
+        cudaFreeHost(idx->h_stage_buf[b]);
+        cudaFreeHost(idx->h_labels_buf[b]);
+        if (idx->stage_done[b]) cudaEventDestroy(idx->stage_done[b]);
+    }
     cudaFree(idx->d_queries);
     cudaFreeHost(idx->h_queries);
     cudaFree(idx->d_labels_out);
@@ -613,7 +653,7 @@ int dawn_index_add_batch(dawn_index *idx, const uint64_t *labels, const float *v
         idx->staged += take;
         done += take;
         if (idx->staged == kStageRowsHost) {
-            rc = flush_staged(idx);
+            rc = flush_staged_async(idx);  // the next chunk is copied on the host while this one moves
             if (rc) return rc;
         }
     }

@@ -698,8 +698,15 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
         select_topk_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, thr, overflow, kSelCap, p.kprime, p.labels, nullptr);
     }
     int launches = 2;
-    // rounds of rows: [0,1024), then x8 each time (~7k' survivors per query per round); every
-    // boundary is a multiple of the tile height
+    // rounds of rows: [0,1024), then x`growth` each time ((growth-1)*k' survivors per query per
+    // round, which must fit the 2048-entry log with margin); every boundary is a multiple of the
+    // tile height.  Compute-bound batches use x8 (fewest survivors to handle); HBM-bound batches
+    // (one query tile: the epilogue has slack) use up to x32 to save rounds.
+    uint64_t growth = 8;
+    if (n_qtiles == 1 && cg == 1) {
+        growth = 32;
+        while (growth > 8 && (growth - 1) * (uint64_t)p.kprime * 5 / 4 + (uint64_t)p.kprime > (uint64_t)kSelCap) growth /= 2;
+    }
     uint64_t begin = 0, end = 1024;
     while (begin < p.n_rows) {
         if (end > p.n_rows || end + end / 4 > p.n_rows) end = p.n_rows;  // fold a short last round into this one
@@ -719,7 +726,7 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
                                                       last ? p.final_lists : nullptr);
         launches += 2;
         begin = end;
-        end = end * 8;
+        end = end * growth;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (p.eps_out) *p.eps_out = eps_q;

@@ -357,3 +357,27 @@ def test_auto_path_selection(index300k, oracle):
     idx.search_batch(oracle.make_queries(SEED, 2, 64, n), 10)
     p = idx.profile(reset=True)
     assert p["gemm_batches"] == 1 and p["scan_launches"] == 0
+
+
+def test_gemm_path_adversarial_row_order_falls_back_exactly(dawn, oracle):
+    """Rows ordered so that thousands of near neighbours of the query come LAST: the thresholds
+    learnt from earlier rounds are useless, the per-query candidate log overflows, the query is
+    flagged and re-run through the exact scan.  The answer must still be bit-identical."""
+    n_bg, n_hot = 70_000, 6_000
+    bg = oracle.np_synth_rows_f32(8, 0, n_bg)
+    q = oracle.np_synth_rows_f32(9, 0, 1)[0]
+    noise = oracle.np_synth_rows_f32(10, 0, n_hot)
+    hot = q[None, :] + 0.3 * noise
+    hot = (hot / np.linalg.norm(hot, axis=1, keepdims=True)).astype(np.float32)
+    rows = np.concatenate([bg, hot])
+    n = len(rows)
+    stored = oracle.store_f16(rows)
+    with dawn.new_index(dawn.IndexOptions(capacity=n)) as idx:
+        idx.add_batch(np.arange(1, n + 1, dtype=np.uint64), rows)
+        idx.set_option("force_path", 2)
+        qs = np.stack([q] + list(oracle.make_queries(8, 11, 3, n_bg)))
+        gl, gd, cnt = idx.search_batch(qs, 10)
+        prof = idx.profile()
+        assert prof["gemm_batches"] == 1 and prof["escalations"] >= 1  # query 0 overflowed its log
+        wl, wd, wc, _ = oracle.cpu_scan_f16(stored, None, qs, 10)
+        assert (gl == wl).all() and (bits(gd) == bits(wd)).all()
