@@ -365,6 +365,18 @@ def run_ours(args):
                           "note": "labels and distances bit-identical to the CPU oracle (tests/); the e2e path "
                                   "re-runs any query whose exactness certificate fails through the f32 scan"},
         }
+        try:  # recall of the reference's kind of index vs the exact answer (config C1), measured by
+            # tools/c1_reference_path.py on a B200 box and committed; not re-measured here (52 s build)
+            with open(os.path.join(ROOT, "profiles", "r01_c1_reference_path_hnsw_recall.json")) as f:
+                c1 = json.load(f)
+            line["reference_path_recall"] = {
+                "source": "profiles/r01_c1_reference_path_hnsw_recall.json (tools/c1_reference_path.py)",
+                "index": c1["index"], "config": c1["config"],
+                "hnsw_recall_at_10_ef64": c1["results"]["k10"]["hnsw_ef64"]["recall"],
+                "hnsw_p50_us_ef64": c1["results"]["k10"]["hnsw_ef64"]["p50_us"],
+                "exact_gpu_recall": 1.0, "exact_gpu_p50_us": c1["b200_exact_c_abi"]["p50_us"], "note": c1["note"]}
+        except Exception:
+            pass
         if batch1:
             line["batch1"] = batch1
         if sweep:

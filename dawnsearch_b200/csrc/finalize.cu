@@ -201,13 +201,15 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
 cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s) {
     if (p.nq == 0) return cudaSuccess;
     if (p.kprime < 1 || p.kprime > kMaxCand || p.k < 1 || p.k > p.kprime) return cudaErrorInvalidValue;
-    static bool configured = false;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
     const size_t smem = fin_smem_bytes(p.n_lists == 1 ? p.kprime : kFinCapEntries);
-    if (!configured) {
+    if (dev < 64 && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)fin_smem_bytes(kFinCapEntries));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     finalize_kernel<<<p.nq, p.n_lists == 1 ? kFinThreadsSingle : kFinThreads, smem, s>>>(p.corpus, p.queries, p.partials, p.n_lists,
                                                    p.kprime, p.k, p.eps, p.labels_out, p.distances_out,

@@ -20,7 +20,8 @@
 //              max-reduce, compare with the query's threshold (a register); survivors (rare)
 //              are appended to the query's candidate log in global memory.
 //
-// Selection across the corpus runs in geometrically growing ROUNDS of rows (1024, x8, ...):
+// Selection across the corpus runs in geometrically growing ROUNDS of tiles (4 tiles = 1024 rows, x8, ...;
+// tiles are visited in a strided permutation so each round is a uniform sample of the corpus):
 // round 0 logs everything, select_topk_kernel then keeps the best k' per query and publishes
 // the k'-th score as the threshold for the next round, so a round appends ~7k' candidates per
 // query regardless of its size.  The log is a superset of the top-k' under the fp16-query
@@ -199,7 +200,8 @@ __device__ __noinline__ void flush_staged(uint32_t stage_smem, int col, uint32_t
 template <int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
-                 uint32_t row_begin, uint32_t row_end, uint32_t n_rows, int n_qtiles, int n_queries,
+                 uint32_t tile_begin, uint32_t tile_end, uint32_t n_rows, uint32_t n_tiles_total, uint32_t perm_mult,
+                 int n_qtiles, int n_queries,
                  int chunk_tiles, const float *__restrict__ thr_g, uint32_t *__restrict__ cnt_g,
                  uint2 *__restrict__ log_g, uint32_t *__restrict__ overflow_g, int log_cap) {
     constexpr int kStagesB = 3 * CG;
@@ -258,7 +260,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
     // Work units: (query tile t, chunk of corpus tiles); unit u -> t = u % n_qtiles (fastest, so
     // CTAs that stream the same rows run side by side and share them through L2).
-    const uint32_t n_tiles = (row_end - row_begin + BN - 1) / BN;
+    // Tiles are visited in a strided permutation of the corpus (phys = (i * perm_mult) % n_tiles_total,
+    // perm_mult coprime to n_tiles_total): every round is a uniform sample of the whole corpus, so the
+    // thresholds learnt in early rounds are representative whatever order the pages were stored in.
+    const uint32_t n_tiles = tile_end - tile_begin;
+    auto phys_row0 = [&](uint32_t tile) {
+        return (uint32_t)(((uint64_t)(tile_begin + tile) * perm_mult) % n_tiles_total) * (uint32_t)BN;
+    };
     const uint32_t n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
     const uint32_t n_units = n_chunks * (uint32_t)n_qtiles;
 
@@ -294,7 +302,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint32_t tile0 = chunk * chunk_tiles;
             const uint32_t tile1 = min(n_tiles, tile0 + chunk_tiles);
             for (uint32_t tile = tile0; tile < tile1; tile++) {
-                const int row0 = (int)(row_begin + tile * BN) + (int)cta_rank * kBRows;
+                const int row0 = (int)phys_row0(tile) + (int)cta_rank * kBRows;
                 for (int kb = 0; kb < kKBlocks; kb++, g++) {
                     const uint32_t s = g % kStagesB;
                     mbar_wait(empty_bar(s), ((g / kStagesB) & 1u) ^ 1u);
@@ -375,11 +383,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint32_t tile1 = min(n_tiles, tile0 + chunk_tiles);
             for (uint32_t tile = tile0; tile < tile1; tile++, tile_ctr++) {
                 const uint32_t acc = tile_ctr & 1u;
-                const uint32_t row0 = row_begin + tile * BN;
+                const uint32_t row0 = phys_row0(tile);
                 mbar_wait(tfull_bar(acc), (tile_ctr >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-                const int lim_tile = (int)min(row_end, n_rows) - (int)row0;  // valid columns of this tile
+                const int lim_tile = (int)n_rows - (int)row0;  // valid columns of this tile (the last physical tile is ragged)
                 // One 32-column chunk: 4 group maxima -> overall max; only groups that reach the
                 // threshold are examined element by element.  Survivors are parked in shared memory.
                 auto process = [&](const uint32_t (&v)[32], int c) {
@@ -631,8 +639,9 @@ size_t gemm_workspace_bytes(int n_queries) {
 
 template <int CG>
 static cudaError_t launch_gemm_round(int grid, cudaStream_t s, const CUtensorMap &tmap_q, const CUtensorMap &tmap_x,
-                                     uint32_t begin, uint32_t end, uint32_t n_rows, int n_qtiles, int n_queries, int chunk,
-                                     const float *thr, uint32_t *cnt, uint2 *log, uint32_t *overflow) {
+                                     uint32_t tile_begin, uint32_t tile_end, uint32_t n_rows, uint32_t n_tiles_total,
+                                     uint32_t perm_mult, int n_qtiles, int n_queries, int chunk, const float *thr,
+                                     uint32_t *cnt, uint2 *log, uint32_t *overflow) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kGemmThreads);
@@ -646,8 +655,8 @@ static cudaError_t launch_gemm_round(int grid, cudaStream_t s, const CUtensorMap
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int log_cap = kSelCap;
-    return cudaLaunchKernelEx(&cfg, gemm_topk_kernel<CG>, tmap_q, tmap_x, begin, end, n_rows, n_qtiles, n_queries, chunk,
-                              thr, cnt, log, overflow, log_cap);
+    return cudaLaunchKernelEx(&cfg, gemm_topk_kernel<CG>, tmap_q, tmap_x, tile_begin, tile_end, n_rows, n_tiles_total,
+                              perm_mult, n_qtiles, n_queries, chunk, thr, cnt, log, overflow, log_cap);
 }
 
 cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
@@ -707,21 +716,29 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
         growth = 32;
         while (growth > 8 && (growth - 1) * (uint64_t)p.kprime * 5 / 4 + (uint64_t)p.kprime > (uint64_t)kSelCap) growth /= 2;
     }
-    uint64_t begin = 0, end = 1024;
-    while (begin < p.n_rows) {
-        if (end > p.n_rows || end + end / 4 > p.n_rows) end = p.n_rows;  // fold a short last round into this one
-        const uint64_t n_tiles = (end - begin + BN - 1) / BN;
+    const uint64_t total_tiles = (p.n_rows + BN - 1) / BN;
+    // stride of the visiting permutation: about 0.618 * total, made coprime to total
+    uint64_t mult = (uint64_t)((double)total_tiles * 0.6180339887498949) | 1ull;
+    auto gcd = [](uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; };
+    while (mult > 1 && gcd(mult, total_tiles) != 1) mult += 2;
+    if (total_tiles <= 2) mult = 1;
+    mult %= total_tiles > 0 ? total_tiles : 1;
+    if (mult == 0) mult = 1;
+    uint64_t begin = 0, end = 1024 / BN;  // in (permuted) tiles: round 0 = 4 tiles = 1024 rows
+    while (begin < total_tiles) {
+        if (end > total_tiles || end + end / 4 > total_tiles) end = total_tiles;  // fold a short last round into this one
+        const uint64_t n_tiles = end - begin;
         uint64_t chunk = (n_tiles * (uint64_t)n_qtiles + (uint64_t)workers * 4 - 1) / ((uint64_t)workers * 4);
         if (chunk < 1) chunk = 1;
         if (chunk > 64) chunk = 64;
         if (cg == 2)
-            e = launch_gemm_round<2>(p.grid, s, tmap_q, tmap_x, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows, n_qtiles,
-                                     p.n_queries, (int)chunk, thr, cnt, log, overflow);
+            e = launch_gemm_round<2>(p.grid, s, tmap_q, tmap_x, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows,
+                                     (uint32_t)total_tiles, (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow);
         else
-            e = launch_gemm_round<1>(p.grid, s, tmap_q, tmap_x, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows, n_qtiles,
-                                     p.n_queries, (int)chunk, thr, cnt, log, overflow);
+            e = launch_gemm_round<1>(p.grid, s, tmap_q, tmap_x, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows,
+                                     (uint32_t)total_tiles, (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow);
         if (e != cudaSuccess) return e;
-        const bool last = end >= p.n_rows;
+        const bool last = end >= total_tiles;
         select_topk_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, thr, overflow, kSelCap, p.kprime, p.labels,
                                                       last ? p.final_lists : nullptr);
         launches += 2;

@@ -359,10 +359,11 @@ def test_auto_path_selection(index300k, oracle):
     assert p["gemm_batches"] == 1 and p["scan_launches"] == 0
 
 
-def test_gemm_path_adversarial_row_order_falls_back_exactly(dawn, oracle):
-    """Rows ordered so that thousands of near neighbours of the query come LAST: the thresholds
-    learnt from earlier rounds are useless, the per-query candidate log overflows, the query is
-    flagged and re-run through the exact scan.  The answer must still be bit-identical."""
+def test_gemm_path_adversarial_row_order_stays_exact(dawn, oracle):
+    """Rows stored so that thousands of near neighbours of the query come LAST.  With sequential
+    rounds the thresholds learnt early would be useless and the candidate log would overflow (the
+    overflow -> exact-scan fallback was verified that way); the strided tile permutation makes every
+    round a uniform sample, so the tensor-core path copes.  Either way the answer is bit-identical."""
     n_bg, n_hot = 70_000, 6_000
     bg = oracle.np_synth_rows_f32(8, 0, n_bg)
     q = oracle.np_synth_rows_f32(9, 0, 1)[0]
@@ -378,6 +379,6 @@ def test_gemm_path_adversarial_row_order_falls_back_exactly(dawn, oracle):
         qs = np.stack([q] + list(oracle.make_queries(8, 11, 3, n_bg)))
         gl, gd, cnt = idx.search_batch(qs, 10)
         prof = idx.profile()
-        assert prof["gemm_batches"] == 1 and prof["escalations"] >= 1  # query 0 overflowed its log
+        assert prof["gemm_batches"] == 1 and prof["uncertified"] == 0
         wl, wd, wc, _ = oracle.cpu_scan_f16(stored, None, qs, 10)
         assert (gl == wl).all() and (bits(gd) == bits(wd)).all()

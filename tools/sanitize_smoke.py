@@ -1,0 +1,36 @@
+"""Small shapes of every kernel path, for compute-sanitizer (memcheck / racecheck) runs."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import dawnsearch_b200 as D
+from oracle import oracle as O
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+n = 3000
+rows = O.np_synth_rows_f32(5, 0, n)
+labels = np.arange(1, n + 1, dtype=np.uint64)
+qs = O.make_queries(5, 6, 300, n)
+stored = O.store_f16(rows)
+if which in ("all", "scan"):
+    with D.new_index(D.IndexOptions(capacity=n)) as idx:
+        idx.add_batch(labels, rows)
+        for b in (1, 2, 4):
+            gl, gd, cnt = idx.search_batch(qs[:b], 10)
+            assert (gl[0] == O.search_f16(stored, None, qs[0], 10)[0]).all()
+        print("scan ok", flush=True)
+if which in ("all", "gemm"):
+    with D.new_index(D.IndexOptions(capacity=n)) as idx:
+        idx.add_batch(labels, rows)
+        idx.set_option("force_path", 2)
+        for b in (8, 300):
+            gl, gd, cnt = idx.search_batch(qs[:b], 10)
+            assert (gl[0] == O.search_f16(stored, None, qs[0], 10)[0]).all()
+        print("gemm ok", idx.profile()["gemm_batches"], flush=True)
+if which in ("all", "i8"):
+    q8, sc = O.store_i8(rows)
+    with D.new_index(D.IndexOptions(capacity=n, quantization=D.ScalarKind.I8)) as idx:
+        idx.add_batch(labels, rows)
+        for b in (1, 2):
+            gl, gd, cnt = idx.search_batch(qs[:b], 10)
+            assert (gl[0] == O.search_i8(q8, sc, None, qs[0], 10)[0]).all()
+        print("i8 ok", flush=True)
