@@ -1,0 +1,394 @@
+// dawn_multi.cu -- the multi-GPU layer for a SINGLE-PROCESS caller (the reference binary is one
+// process, /root/reference/src/bin/dawnsearch.rs): the corpus is sharded over the GPUs of one box,
+// every GPU answers the batch from its shard, the per-shard result blocks are pushed over NVLink
+// into GPU 0's memory (peer copies: one small message per shard, the shape of the reference's
+// scatter / gather / merge across WAN peers, src/net/udp_service.rs:314-330 and
+// src/search/search_service.rs:201-277), and merged there by merge_results_kernel.
+// (The one-process-per-GPU variant of the same exchange, with an NCCL all-gather, is
+// dawnsearch_b200/sharded.py.)
+//
+// Exactness: shards return bit-exact distances, the merge orders by (distance, label), so the
+// answer equals a single index holding everything.  Queries a shard could not certify are re-run
+// on that shard through the exact scan before the merge.
+#include <condition_variable>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/dawn_index.h"
+
+namespace {
+
+thread_local std::string g_multi_err;
+
+struct Shard {
+    int device = 0;
+    dawn_index *idx = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    // per-call device buffers (grown on demand)
+    float *d_q = nullptr;
+    uint8_t *d_block = nullptr;
+    uint32_t *d_flags = nullptr;
+    uint32_t *h_flags = nullptr;  // pinned
+    float *h_q = nullptr;         // pinned copy of the queries for this device
+    size_t q_cap = 0, block_cap = 0;
+    // worker thread
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool has_job = false, stop = false;
+    int rc = 0;
+    std::string err;
+    bool job_done = false;
+};
+
+size_t block_bytes(size_t batch, size_t k) { return (batch * k * 12 + batch * 4 + 15) / 16 * 16; }
+
+}  // namespace
+
+struct dawn_multi {
+    std::vector<Shard *> shards;
+    std::mutex mu;
+    uint32_t scalar = DAWN_SCALAR_F16;
+    // device 0 side
+    uint8_t *d_gather = nullptr, *d_out = nullptr;
+    uint8_t *h_out = nullptr;
+    size_t gather_cap = 0, out_cap = 0;
+    size_t next_shard = 0;  // round-robin cursor for add
+};
+
+namespace {
+
+void worker_loop(Shard *s) {
+    cudaSetDevice(s->device);
+    std::unique_lock<std::mutex> lk(s->mu);
+    while (true) {
+        s->cv.wait(lk, [&] { return s->has_job || s->stop; });
+        if (s->stop) return;
+        auto job = s->job;
+        lk.unlock();
+        g_multi_err.clear();
+        int rc = job();
+        std::string err = rc ? (g_multi_err.empty() ? std::string(dawn_last_error()) : g_multi_err) : std::string();
+        lk.lock();
+        s->rc = rc;
+        s->err = err;
+        s->has_job = false;
+        s->job_done = true;
+        s->cv.notify_all();
+    }
+}
+
+void submit(Shard *s, std::function<int()> job) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->job = std::move(job);
+    s->has_job = true;
+    s->job_done = false;
+    s->cv.notify_all();
+}
+
+int wait(Shard *s) {
+    std::unique_lock<std::mutex> lk(s->mu);
+    s->cv.wait(lk, [&] { return s->job_done; });
+    if (s->rc) g_multi_err = s->err;
+    return s->rc;
+}
+
+int run_all(dawn_multi *m, const std::function<int(Shard *, size_t)> &fn) {
+    for (size_t g = 0; g < m->shards.size(); g++) {
+        Shard *s = m->shards[g];
+        submit(s, [=] { return fn(s, g); });
+    }
+    int rc = DAWN_OK;
+    for (Shard *s : m->shards) {
+        int r = wait(s);
+        if (r && !rc) rc = r;
+    }
+    return rc;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    g_multi_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return DAWN_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *dawn_multi_last_error(void) { return g_multi_err.c_str(); }
+
+int dawn_multi_create(const int *devices, size_t n_devices, uint32_t scalar, dawn_multi **out) {
+    if (!devices || n_devices == 0 || n_devices > 64 || !out) return DAWN_ERR_INVALID;
+    dawn_multi *m = new (std::nothrow) dawn_multi();
+    if (!m) return DAWN_ERR_INTERNAL;
+    m->scalar = scalar;
+    for (size_t g = 0; g < n_devices; g++) {
+        Shard *s = new Shard();
+        s->device = devices[g];
+        dawn_options o{};
+        o.dimensions = DAWN_DIMENSIONS;
+        o.scalar = scalar;
+        o.device = devices[g];
+        int rc = dawn_index_create(&o, &s->idx);
+        if (rc == DAWN_OK) {
+            cudaError_t e = cudaSetDevice(s->device);
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
+            if (e != cudaSuccess) rc = cuda_fail(e, "shard setup");
+        } else {
+            g_multi_err = dawn_last_error();
+        }
+        m->shards.push_back(s);
+        if (rc != DAWN_OK) {
+            dawn_multi_free(m);
+            return rc;
+        }
+        s->th = std::thread(worker_loop, s);
+    }
+    *out = m;
+    return DAWN_OK;
+}
+
+void dawn_multi_free(dawn_multi *m) {
+    if (!m) return;
+    for (Shard *s : m->shards) {
+        if (s->th.joinable()) {
+            {
+                std::lock_guard<std::mutex> lk(s->mu);
+                s->stop = true;
+            }
+            s->cv.notify_all();
+            s->th.join();
+        }
+        cudaSetDevice(s->device);
+        cudaFree(s->d_q);
+        cudaFree(s->d_block);
+        cudaFree(s->d_flags);
+        cudaFreeHost(s->h_flags);
+        cudaFreeHost(s->h_q);
+        if (s->done) cudaEventDestroy(s->done);
+        if (s->stream) cudaStreamDestroy(s->stream);
+        dawn_index_free(s->idx);
+        delete s;
+    }
+    if (!m->shards.empty()) cudaSetDevice(m->shards[0]->device);
+    cudaFree(m->d_gather);
+    cudaFree(m->d_out);
+    cudaFreeHost(m->h_out);
+    cudaGetLastError();
+    delete m;
+}
+
+size_t dawn_multi_shards(const dawn_multi *m) { return m ? m->shards.size() : 0; }
+
+size_t dawn_multi_size(const dawn_multi *m) {
+    size_t n = 0;
+    if (m)
+        for (Shard *s : m->shards) n += dawn_index_size(s->idx);
+    return n;
+}
+
+size_t dawn_multi_capacity(const dawn_multi *m) {
+    size_t n = 0;
+    if (m)
+        for (Shard *s : m->shards) n += dawn_index_capacity(s->idx);
+    return n;
+}
+
+// Capacity is split evenly over the shards.
+int dawn_multi_reserve(dawn_multi *m, size_t n_total) {
+    if (!m) return DAWN_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(m->mu);
+    const size_t per = (n_total + m->shards.size() - 1) / m->shards.size();
+    for (Shard *s : m->shards) {
+        int rc = dawn_index_reserve(s->idx, per);
+        if (rc) {
+            g_multi_err = dawn_last_error();
+            return rc;
+        }
+    }
+    return DAWN_OK;
+}
+
+// Appends go to the shards in blocks, round-robin, skipping full shards (labels travel with the
+// vectors, so any placement gives the same answers).
+int dawn_multi_add_batch(dawn_multi *m, const uint64_t *labels, const float *vectors, size_t n) {
+    if (!m || (n && (!labels || !vectors))) return DAWN_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(m->mu);
+    const size_t kBlock = 4096;
+    size_t done = 0;
+    while (done < n) {
+        size_t tries = 0;
+        Shard *s = nullptr;
+        size_t room = 0;
+        while (tries < m->shards.size()) {
+            s = m->shards[m->next_shard % m->shards.size()];
+            room = dawn_index_capacity(s->idx) - dawn_index_size(s->idx);
+            if (room > 0) break;
+            m->next_shard++;
+            tries++;
+        }
+        if (room == 0) {
+            g_multi_err = "add exceeds the reserved capacity of every shard: reserve first";
+            return DAWN_ERR_CAPACITY;
+        }
+        size_t take = n - done < kBlock ? n - done : kBlock;
+        if (take > room) take = room;
+        int rc = dawn_index_add_batch(s->idx, labels + done, vectors + done * DAWN_DIMENSIONS, take);
+        if (rc) {
+            g_multi_err = dawn_last_error();
+            return rc;
+        }
+        done += take;
+        m->next_shard++;
+    }
+    return DAWN_OK;
+}
+
+int dawn_multi_add(dawn_multi *m, uint64_t label, const float *vector384) {
+    return dawn_multi_add_batch(m, &label, vector384, 1);
+}
+
+// Synthetic corpus rows [first_row, first_row+n) split into contiguous id ranges, one per shard.
+int dawn_multi_add_synthetic(dawn_multi *m, uint64_t seed, uint64_t first_row, size_t n) {
+    if (!m) return DAWN_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(m->mu);
+    const size_t G = m->shards.size();
+    const size_t per = (n + G - 1) / G;
+    return run_all(m, [=](Shard *s, size_t g) -> int {
+        const size_t a = g * per < n ? g * per : n;
+        const size_t cnt = a + per < n ? per : n - a;
+        if (cnt == 0) return DAWN_OK;
+        return dawn_index_add_synthetic(s->idx, seed, first_row + a, cnt);
+    });
+}
+
+int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, size_t k, uint64_t *labels_out,
+                            float *distances_out, size_t *counts_out) {
+    if (!m || !queries || !counts_out || (k && (!labels_out || !distances_out))) return DAWN_ERR_INVALID;
+    if (batch == 0) return DAWN_OK;
+    if (k == 0) {
+        for (size_t b = 0; b < batch; b++) counts_out[b] = 0;
+        return DAWN_OK;
+    }
+    if (k > DAWN_MAX_K || m->shards.size() * k > 1024) {
+        g_multi_err = "k too large for this many shards (shards * k must be <= 1024)";
+        return DAWN_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(m->mu);
+    const size_t G = m->shards.size();
+    const size_t bb = block_bytes(batch, k);
+    const size_t off_d = batch * k * 8, off_c = off_d + batch * k * 4;
+    Shard *s0 = m->shards[0];
+    cudaError_t e = cudaSetDevice(s0->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    if (G * bb > m->gather_cap) {
+        cudaFree(m->d_gather);
+        m->gather_cap = 0;
+        if ((e = cudaMalloc(&m->d_gather, G * bb)) != cudaSuccess) return cuda_fail(e, "cudaMalloc gather");
+        m->gather_cap = G * bb;
+    }
+    if (bb > m->out_cap) {
+        cudaFree(m->d_out);
+        cudaFreeHost(m->h_out);
+        m->out_cap = 0;
+        if ((e = cudaMalloc(&m->d_out, bb)) != cudaSuccess) return cuda_fail(e, "cudaMalloc out");
+        if ((e = cudaMallocHost(&m->h_out, bb)) != cudaSuccess) return cuda_fail(e, "cudaMallocHost out");
+        m->out_cap = bb;
+    }
+    uint8_t *d_gather = m->d_gather;
+    const int dev0 = s0->device;
+
+    // every shard: H2D queries, local exact top-k into a packed block, push the block to GPU 0
+    int rc = run_all(m, [=](Shard *s, size_t g) -> int {
+        cudaError_t ce;
+        if (batch > s->q_cap) {
+            cudaFree(s->d_q);
+            cudaFree(s->d_flags);
+            cudaFreeHost(s->h_flags);
+            cudaFreeHost(s->h_q);
+            s->q_cap = 0;
+            const size_t cap = batch < 64 ? 64 : batch;
+            if ((ce = cudaMalloc(&s->d_q, cap * DAWN_DIMENSIONS * sizeof(float))) != cudaSuccess) return cuda_fail(ce, "cudaMalloc q");
+            if ((ce = cudaMalloc(&s->d_flags, cap * sizeof(uint32_t))) != cudaSuccess) return cuda_fail(ce, "cudaMalloc flags");
+            if ((ce = cudaMallocHost(&s->h_flags, cap * sizeof(uint32_t))) != cudaSuccess) return cuda_fail(ce, "cudaMallocHost flags");
+            if ((ce = cudaMallocHost(&s->h_q, cap * DAWN_DIMENSIONS * sizeof(float))) != cudaSuccess) return cuda_fail(ce, "cudaMallocHost q");
+            s->q_cap = cap;
+        }
+        if (bb > s->block_cap) {
+            cudaFree(s->d_block);
+            s->block_cap = 0;
+            if ((ce = cudaMalloc(&s->d_block, bb)) != cudaSuccess) return cuda_fail(ce, "cudaMalloc block");
+            s->block_cap = bb;
+        }
+        memcpy(s->h_q, queries, batch * DAWN_DIMENSIONS * sizeof(float));
+        if ((ce = cudaMemcpyAsync(s->d_q, s->h_q, batch * DAWN_DIMENSIONS * sizeof(float), cudaMemcpyHostToDevice, s->stream)) != cudaSuccess)
+            return cuda_fail(ce, "H2D queries");
+        if ((ce = cudaMemsetAsync(s->d_block, 0, bb, s->stream)) != cudaSuccess) return cuda_fail(ce, "memset block");
+        int r = dawn_index_search_device(s->idx, s->d_q, batch, k, reinterpret_cast<uint64_t *>(s->d_block),
+                                         reinterpret_cast<float *>(s->d_block + off_d),
+                                         reinterpret_cast<uint32_t *>(s->d_block + off_c), s->d_flags, s->stream);
+        if (r) return r;
+        if ((ce = cudaMemcpyAsync(s->h_flags, s->d_flags, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess)
+            return cuda_fail(ce, "D2H flags");
+        if ((ce = cudaStreamSynchronize(s->stream)) != cudaSuccess) return cuda_fail(ce, "shard sync");
+        // queries this shard could not certify: exact re-run through the host API, patched into the block
+        if (dawn_index_size(s->idx) > 0) {
+            std::vector<uint64_t> l(k);
+            std::vector<float> d(k);
+            for (size_t b = 0; b < batch; b++) {
+                if (s->h_flags[b] & 1u) continue;
+                size_t cnt = 0;
+                r = dawn_index_search(s->idx, queries + b * DAWN_DIMENSIONS, k, l.data(), d.data(), &cnt);
+                if (r) return r;
+                uint32_t c32 = (uint32_t)cnt;
+                cudaMemcpyAsync(s->d_block + b * k * 8, l.data(), cnt * 8, cudaMemcpyHostToDevice, s->stream);
+                cudaMemcpyAsync(s->d_block + off_d + b * k * 4, d.data(), cnt * 4, cudaMemcpyHostToDevice, s->stream);
+                cudaMemcpyAsync(s->d_block + off_c + b * 4, &c32, 4, cudaMemcpyHostToDevice, s->stream);
+                if ((ce = cudaStreamSynchronize(s->stream)) != cudaSuccess) return cuda_fail(ce, "patch sync");
+            }
+        }
+        // one message per shard over NVLink into GPU 0's gather buffer
+        if ((ce = cudaMemcpyPeerAsync(d_gather + g * bb, dev0, s->d_block, s->device, bb, s->stream)) != cudaSuccess)
+            return cuda_fail(ce, "peer copy");
+        if ((ce = cudaStreamSynchronize(s->stream)) != cudaSuccess) return cuda_fail(ce, "peer sync");
+        return DAWN_OK;
+    });
+    if (rc) return rc;
+
+    // device-side merge on GPU 0, then one D2H of the merged block
+    if ((e = cudaSetDevice(dev0)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    rc = dawn_merge_results_device(dev0, reinterpret_cast<uint64_t *>(d_gather), reinterpret_cast<float *>(d_gather + off_d),
+                                   reinterpret_cast<uint32_t *>(d_gather + off_c), G, bb, batch, k,
+                                   reinterpret_cast<uint64_t *>(m->d_out), reinterpret_cast<float *>(m->d_out + off_d),
+                                   reinterpret_cast<uint32_t *>(m->d_out + off_c), s0->stream);
+    if (rc) {
+        g_multi_err = dawn_last_error();
+        return rc;
+    }
+    if ((e = cudaMemcpyAsync(m->h_out, m->d_out, bb, cudaMemcpyDeviceToHost, s0->stream)) != cudaSuccess) return cuda_fail(e, "D2H out");
+    if ((e = cudaStreamSynchronize(s0->stream)) != cudaSuccess) return cuda_fail(e, "final sync");
+    const uint32_t *cnt = reinterpret_cast<const uint32_t *>(m->h_out + off_c);
+    for (size_t b = 0; b < batch; b++) {
+        counts_out[b] = cnt[b];
+        memcpy(labels_out + b * k, m->h_out + b * k * 8, cnt[b] * 8);
+        memcpy(distances_out + b * k, m->h_out + off_d + b * k * 4, cnt[b] * 4);
+    }
+    return DAWN_OK;
+}
+
+int dawn_multi_search(dawn_multi *m, const float *query384, size_t k, uint64_t *labels_out, float *distances_out,
+                      size_t *count_out) {
+    return dawn_multi_search_batch(m, query384, 1, k, labels_out, distances_out, count_out);
+}
+
+}  // extern "C"

@@ -152,6 +152,19 @@ def load_library() -> C.CDLL:
     L.dawn_batcher_last_error.restype = C.c_char_p
     L.dawn_batcher_free.argtypes = [_vp]
     L.dawn_batcher_free.restype = None
+    L.dawn_multi_create.argtypes = [_vp, C.c_size_t, C.c_uint32, C.POINTER(_vp)]
+    L.dawn_multi_free.argtypes = [_vp]
+    L.dawn_multi_free.restype = None
+    L.dawn_multi_reserve.argtypes = [_vp, C.c_size_t]
+    L.dawn_multi_add.argtypes = [_vp, C.c_uint64, _vp]
+    L.dawn_multi_add_batch.argtypes = [_vp, _vp, _vp, C.c_size_t]
+    L.dawn_multi_add_synthetic.argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_size_t]
+    L.dawn_multi_search.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp, _vp]
+    L.dawn_multi_search_batch.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp]
+    for name in ("dawn_multi_size", "dawn_multi_capacity", "dawn_multi_shards"):
+        getattr(L, name).argtypes = [_vp]
+        getattr(L, name).restype = C.c_size_t
+    L.dawn_multi_last_error.restype = C.c_char_p
     _lib = L
     return L
 
@@ -382,6 +395,80 @@ class Batcher:
             self.close()
         except Exception:
             pass
+
+
+class MultiIndex:
+    """Several GPUs, one process: one shard per listed device, searched concurrently, merged on the
+    first device (include/dawn_index.h: dawn_multi_*).  Same method names as `Index`."""
+
+    def __init__(self, devices, quantization: int = ScalarKind.F16):
+        self._L = load_library()
+        dev = (C.c_int * len(devices))(*devices)
+        h = _vp()
+        self._check(self._L.dawn_multi_create(dev, len(devices), quantization, C.byref(h)))
+        self._h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            raise DawnError(rc, self._L.dawn_multi_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dawn_multi_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reserve(self, capacity: int) -> None:
+        self._check(self._L.dawn_multi_reserve(self._h, capacity))
+
+    def add(self, label: int, vector) -> None:
+        v = np.ascontiguousarray(vector, dtype=np.float32)
+        self._check(self._L.dawn_multi_add(self._h, int(label), _ptr(v)))
+
+    def add_batch(self, labels, vectors) -> None:
+        lab = np.ascontiguousarray(labels, dtype=np.uint64)
+        v = np.ascontiguousarray(vectors, dtype=np.float32).reshape(-1, EM_LEN)
+        self._check(self._L.dawn_multi_add_batch(self._h, _ptr(lab), _ptr(v), v.shape[0]))
+
+    def add_synthetic(self, seed: int, first_row: int, n: int) -> None:
+        self._check(self._L.dawn_multi_add_synthetic(self._h, seed, first_row, n))
+
+    def search(self, query, count: int) -> Matches:
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        labels = np.zeros(max(count, 1), dtype=np.uint64)
+        dist = np.zeros(max(count, 1), dtype=np.float32)
+        n = C.c_size_t(0)
+        self._check(self._L.dawn_multi_search(self._h, _ptr(q), count, _ptr(labels), _ptr(dist), C.byref(n)))
+        return Matches(labels[: n.value].copy(), dist[: n.value].copy())
+
+    def search_batch(self, queries, count: int):
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, EM_LEN)
+        b = q.shape[0]
+        labels = np.zeros((b, max(count, 1)), dtype=np.uint64)
+        dist = np.zeros((b, max(count, 1)), dtype=np.float32)
+        counts = np.zeros(b, dtype=np.uint64)
+        self._check(self._L.dawn_multi_search_batch(self._h, _ptr(q), b, count, _ptr(labels), _ptr(dist), _ptr(counts)))
+        return labels, dist, counts.astype(np.int64)
+
+    def size(self) -> int:
+        return int(self._L.dawn_multi_size(self._h))
+
+    def capacity(self) -> int:
+        return int(self._L.dawn_multi_capacity(self._h))
+
+    def shards(self) -> int:
+        return int(self._L.dawn_multi_shards(self._h))
 
 
 def new_index(options: IndexOptions | None = None) -> Index:

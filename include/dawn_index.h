@@ -175,6 +175,28 @@ int dawn_batcher_stats(dawn_batcher *b, uint64_t *batches, uint64_t *queries, ui
 const char *dawn_batcher_last_error(void);
 void dawn_batcher_free(dawn_batcher *b);
 
+/* ---- several GPUs, one process (the reference binary is one process) ---------------------------
+ * One handle owns one shard per listed device.  add* places blocks of vectors round-robin on the
+ * shards; search* runs every shard's exact top-k concurrently, pushes each shard's packed result
+ * block over NVLink into the first device's memory (one peer copy per shard) and merges there.
+ * Results are bit-identical to a single index holding everything.  (The one-process-per-GPU
+ * variant with an NCCL all-gather is dawnsearch_b200/sharded.py.) */
+typedef struct dawn_multi dawn_multi;
+int dawn_multi_create(const int *devices, size_t n_devices, uint32_t scalar, dawn_multi **out);
+void dawn_multi_free(dawn_multi *m);
+int dawn_multi_reserve(dawn_multi *m, size_t n_total);
+int dawn_multi_add(dawn_multi *m, uint64_t label, const float *vector384);
+int dawn_multi_add_batch(dawn_multi *m, const uint64_t *labels, const float *vectors, size_t n);
+int dawn_multi_add_synthetic(dawn_multi *m, uint64_t seed, uint64_t first_row, size_t n);
+int dawn_multi_search(dawn_multi *m, const float *query384, size_t k, uint64_t *labels_out, float *distances_out,
+                      size_t *count_out);
+int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, size_t k, uint64_t *labels_out,
+                            float *distances_out, size_t *counts_out);
+size_t dawn_multi_size(const dawn_multi *m);
+size_t dawn_multi_capacity(const dawn_multi *m);
+size_t dawn_multi_shards(const dawn_multi *m);
+const char *dawn_multi_last_error(void);
+
 /* ---- instrumentation ------------------------------------------------------------------- */
 typedef struct dawn_profile {
     uint64_t scan_launches;  /* K2 launches since the last reset */

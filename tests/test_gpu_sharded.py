@@ -54,3 +54,58 @@ def test_two_gpu_sharded_search_matches_oracle(tmp_path):
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" ok") == 4, r.stdout
+
+
+def _multi_devices():
+    import torch
+
+    n = torch.cuda.device_count()
+    return [0, 1] if n >= 2 else [0, 0]  # two shards on one GPU still exercise the whole exchange
+
+
+def test_single_process_multi_index_matches_oracle(dawn, oracle):
+    """dawn_multi_*: one process, one shard per device, peer-copy gather + device merge."""
+    import numpy as np
+
+    n = 30_001
+    rows = oracle.np_synth_rows_f32(71, 0, n)
+    labels = (np.argsort(oracle.np_mix64(np.arange(n, dtype=np.uint64) + np.uint64(3)), kind="stable") + 10).astype(np.uint64)
+    stored = oracle.store_f16(rows)
+    with dawn.MultiIndex(_multi_devices()) as m:
+        assert m.shards() == 2
+        m.reserve(n + 10)
+        m.add_batch(labels[:20000], rows[:20000])
+        for i in range(20000, 20010):  # single adds, like SearchProvider::insert
+            m.add(int(labels[i]), rows[i])
+        m.add_batch(labels[20010:], rows[20010:])
+        assert m.size() == n
+        for batch, k in ((1, 20), (5, 10), (40, 100)):
+            qs = oracle.make_queries(71, 72 + batch, batch, n)
+            gl, gd, cnt = m.search_batch(qs, k)
+            wl, wd, wc, _ = oracle.cpu_scan_f16(stored, labels, qs, k)
+            assert (cnt == wc).all() and (gl == wl).all()
+            assert (gd.view(np.uint32) == wd.view(np.uint32)).all()
+        with pytest.raises(dawn.DawnError):
+            m.add_batch(np.arange(100, dtype=np.uint64), np.zeros((100, 384), dtype=np.float32))  # beyond capacity
+
+
+def test_single_process_multi_index_synthetic_and_duplicates(dawn, oracle):
+    import numpy as np
+
+    n = 200_000
+    with dawn.MultiIndex(_multi_devices()) as m:
+        m.reserve(n)
+        m.add_synthetic(0xDA5EA2C4, 0, n)
+        stored = oracle.synth_rows_f16(0xDA5EA2C4, 0, n)
+        qs = oracle.make_queries(0xDA5EA2C4, 5, 24, n)
+        gl, gd, cnt = m.search_batch(qs, 10)
+        wl, wd, wc, _ = oracle.cpu_scan_f16(stored, None, qs, 10)
+        assert (gl == wl).all() and (gd.view(np.uint32) == wd.view(np.uint32)).all()
+    base = oracle.np_synth_rows_f32(5, 0, 1)
+    rows = np.repeat(base, 2000, axis=0)  # every shard full of ties: uncertified -> exact re-run per shard
+    labels = np.arange(2000, 0, -1).astype(np.uint64)
+    with dawn.MultiIndex(_multi_devices()) as m:
+        m.reserve(2000)
+        m.add_batch(labels, rows)
+        r = m.search(base[0], 10)
+        assert list(r.labels) == list(range(1, 11))
