@@ -99,6 +99,7 @@ struct dawn_index {
     int64_t gemm_small_batch_rows = 2000000;
     int64_t force_path = 0;  // 0 auto, 1 scan only, 2 gemm whenever possible
     int64_t gemm_cta_group = 0;  // 0 auto, 1 = one CTA per tile, 2 = CTA pairs
+    int64_t gemm_chunk_tiles = 0;  // 0 auto
 
     bool profiling = false;
     std::vector<EventPair> pending;
@@ -404,6 +405,7 @@ int search_enqueue(dawn_index *idx, const float *d_queries, size_t batch, size_t
         gs.kprime = kprime;
         gs.grid = grid;
         gs.cta_group = (int)idx->gemm_cta_group;
+        gs.chunk_tiles = (int)idx->gemm_chunk_tiles;
         gs.workspace = idx->d_gemm_ws;
         gs.final_lists = idx->d_partials;
         gs.accum_slack = kGemmAccumSlack;
@@ -926,6 +928,7 @@ int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value) {
     else if (!strcmp(key, "gemm_small_batch_rows")) idx->gemm_small_batch_rows = value;
     else if (!strcmp(key, "force_path")) idx->force_path = value;
     else if (!strcmp(key, "gemm_cta_group")) idx->gemm_cta_group = value;
+    else if (!strcmp(key, "gemm_chunk_tiles")) idx->gemm_chunk_tiles = value;
     else return fail(DAWN_ERR_INVALID, "unknown option '%s'", key);
     return DAWN_OK;
 }

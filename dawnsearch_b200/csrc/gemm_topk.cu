@@ -29,6 +29,8 @@
 // eps_q = ||q - fp16(q)|| + accumulation slack (Cauchy-Schwarz, rows have norm <= 1.01).
 #include <cuda.h>
 
+#include <cmath>
+
 #include "dawn_common.cuh"
 
 namespace dawn {
@@ -728,9 +730,12 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
     while (begin < total_tiles) {
         if (end > total_tiles || end + end / 4 > total_tiles) end = total_tiles;  // fold a short last round into this one
         const uint64_t n_tiles = end - begin;
+        // Tiles per work unit: ~4 units per worker for small rounds, at most 64 tiles (A/B on a B200:
+        // 16..100 tiles are equivalent within noise, >= 200 costs ~3 %: tools/ab_gemm.py).
         uint64_t chunk = (n_tiles * (uint64_t)n_qtiles + (uint64_t)workers * 4 - 1) / ((uint64_t)workers * 4);
         if (chunk < 1) chunk = 1;
         if (chunk > 64) chunk = 64;
+        if (p.chunk_tiles > 0) chunk = (uint64_t)p.chunk_tiles;  // tuning override
         if (cg == 2)
             e = launch_gemm_round<2>(p.grid, s, tmap_q, tmap_x, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows,
                                      (uint32_t)total_tiles, (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow);

@@ -1,0 +1,34 @@
+"""A/B of tensor-core-path tuning knobs on ONE GPU in ONE process (boxes differ by several percent)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import dawnsearch_b200 as D
+from dawnsearch_b200 import synth
+
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 50_000_000
+batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+k = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+settings = [dict(gemm_chunk_tiles=c) for c in (16, 32, 48, 64, 96, 100, 200, 219)]
+idx = D.new_index(D.IndexOptions(capacity=rows))
+idx.add_synthetic(0xDA5EA2C4, 0, rows)
+dev = torch.device("cuda:0")
+q = torch.from_numpy(synth.make_queries(0xDA5EA2C4, 3, batch, rows)).to(dev)
+L = torch.zeros((batch, k), dtype=torch.int64, device=dev); Dd = torch.zeros((batch, k), dtype=torch.float32, device=dev)
+Cn = torch.zeros(batch, dtype=torch.int32, device=dev); Fl = torch.zeros(batch, dtype=torch.int32, device=dev)
+def run(n):
+    for _ in range(n):
+        idx.search_device(q.data_ptr(), batch, k, L.data_ptr(), Dd.data_ptr(), Cn.data_ptr(), Fl.data_ptr(), 1)
+    torch.cuda.synchronize()
+run(3)
+res = {}
+for rep in range(3):
+    for st in settings:
+        for kk, v in st.items(): idx.set_option(kk, v)
+        run(1)
+        idx.set_profiling(True); idx.profile(reset=True)
+        run(6)
+        p = idx.profile(reset=True); idx.set_profiling(False)
+        res.setdefault(json.dumps(st), []).append(p["gemm_ms"] / p["gemm_batches"])
+for s, v in res.items():
+    ms = sorted(v)[len(v) // 2]
+    print(s, [round(x, 3) for x in v], "median", round(ms, 3), "TF", round(2 * batch * rows * 384 / ms / 1e9, 1))
