@@ -100,6 +100,7 @@ struct dawn_index {
     int64_t force_path = 0;  // 0 auto, 1 scan only, 2 gemm whenever possible
     int64_t gemm_cta_group = 0;  // 0 auto, 1 = one CTA per tile, 2 = CTA pairs
     int64_t gemm_chunk_tiles = 0;  // 0 auto
+    int64_t gemm_sequential_tiles = 0;
 
     bool profiling = false;
     std::vector<EventPair> pending;
@@ -406,6 +407,7 @@ int search_enqueue(dawn_index *idx, const float *d_queries, size_t batch, size_t
         gs.grid = grid;
         gs.cta_group = (int)idx->gemm_cta_group;
         gs.chunk_tiles = (int)idx->gemm_chunk_tiles;
+        gs.sequential_tiles = (int)idx->gemm_sequential_tiles;
         gs.workspace = idx->d_gemm_ws;
         gs.final_lists = idx->d_partials;
         gs.accum_slack = kGemmAccumSlack;
@@ -929,6 +931,7 @@ int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value) {
     else if (!strcmp(key, "force_path")) idx->force_path = value;
     else if (!strcmp(key, "gemm_cta_group")) idx->gemm_cta_group = value;
     else if (!strcmp(key, "gemm_chunk_tiles")) idx->gemm_chunk_tiles = value;
+    else if (!strcmp(key, "gemm_sequential_tiles")) idx->gemm_sequential_tiles = value;
     else return fail(DAWN_ERR_INVALID, "unknown option '%s'", key);
     return DAWN_OK;
 }

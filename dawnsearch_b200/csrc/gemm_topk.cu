@@ -723,7 +723,7 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
     uint64_t mult = (uint64_t)((double)total_tiles * 0.6180339887498949) | 1ull;
     auto gcd = [](uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; };
     while (mult > 1 && gcd(mult, total_tiles) != 1) mult += 2;
-    if (total_tiles <= 2) mult = 1;
+    if (total_tiles <= 2 || p.sequential_tiles) mult = 1;  // mult = 1: physical order (tuning / A-B only)
     mult %= total_tiles > 0 ? total_tiles : 1;
     if (mult == 0) mult = 1;
     uint64_t begin = 0, end = 1024 / BN;  // in (permuted) tiles: round 0 = 4 tiles = 1024 rows

@@ -8,7 +8,7 @@ from dawnsearch_b200 import synth
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 50_000_000
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 10
-settings = [dict(gemm_chunk_tiles=c) for c in (16, 32, 48, 64, 96, 100, 200, 219)]
+settings = [dict(gemm_sequential_tiles=v) for v in (0, 1)]
 idx = D.new_index(D.IndexOptions(capacity=rows))
 idx.add_synthetic(0xDA5EA2C4, 0, rows)
 dev = torch.device("cuda:0")
