@@ -227,8 +227,12 @@ def run_ours(args):
 
     def timed_device(queries_dev, kk, steps, warm, sample_clocks=False):
         """Device-resident timing: CUDA events on the launching stream + the library's own per-kernel events."""
+        # back-to-back batches: the exchange of batch i overlaps the search of batch i+1 (not worth it
+        # for single queries, where the side-stream bookkeeping costs more than the 12 us exchange)
+        pipe = world > 1 and queries_dev[0].shape[0] >= 16
         for s in range(warm):
-            sh.search_device(queries_dev[s % len(queries_dev)], kk)
+            sh.search_device(queries_dev[s % len(queries_dev)], kk, pipelined=pipe)
+        sh.wait_results()
         barrier()
         sh.index.set_profiling(True)
         sh.index.profile(reset=True)
@@ -239,7 +243,9 @@ def run_ours(args):
         barrier()
         ev[0].record()
         for s in range(steps):
-            sh.search_device(queries_dev[(warm + s) % len(queries_dev)], kk)
+            sh.search_device(queries_dev[(warm + s) % len(queries_dev)], kk, pipelined=pipe)
+            if s == steps - 1:
+                sh.wait_results()  # the last event must cover the last batch's exchange + merge
             ev[s + 1].record()
         barrier()
         clocks = sampler.stop() if sampler else None
@@ -351,6 +357,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args), "rows": args.rows, "rows_per_gpu": n_local,
                        "batch": B, "k": k, "l2": "inputs larger than L2 (corpus shard >> 126 MB), no flush",
+                       "multi_gpu": ("device-resident `value`: the all-gather + merge of batch i run on a side stream "
+                                     "while batch i+1 is searched; e2e: synchronous per call") if world > 1 else None,
                        "corpus_fill_s": round(fill_s, 3)},
             "latency_ms": {"device_step_p50": statistics.median(step_ms), "device_step_max": max(step_ms),
                            "e2e_step_p50": statistics.median(lat),

@@ -64,6 +64,8 @@ class ShardedIndex:
         self.tdev = torch.device("cuda", device)
         self.index: Index = new_index(IndexOptions(device=device, capacity=capacity, quantization=quantization))
         self._ws = {}
+        self._side = None
+        self._last_merged = None
 
     def close(self):
         self.index.close()
@@ -87,26 +89,75 @@ class ShardedIndex:
             self._ws[key] = ws
         return ws
 
-    def search_device(self, d_queries: torch.Tensor, k: int):
+    def search_device(self, d_queries: torch.Tensor, k: int, pipelined: bool = False):
         """Queries already on this rank's GPU ([B,384] f32).  Enqueues local search, the all-gather
-        and the merge on the current stream; returns the packed result block (uint8, device) that
-        `ResultBlock.views` decodes."""
+        and the merge; returns the packed result block (uint8, device) that `ResultBlock.views`
+        decodes.
+
+        pipelined=False: everything is enqueued on the current stream.
+        pipelined=True (back-to-back batches): the exchange + merge of batch i run on a side stream
+        while the current stream already searches batch i+1, so the NCCL latency and the wait for the
+        slowest shard are hidden behind compute; call `wait_results()` before reading the block."""
         batch = d_queries.shape[0]
         ws = self._workspace(batch, k)
         blk: ResultBlock = ws["blk"]
         # torch reports the legacy default stream as 0, which the C ABI reads as "the index's own
         # stream"; cudaStreamLegacy (0x1) names the default stream explicitly.
-        stream = torch.cuda.current_stream(self.tdev).cuda_stream or 1
-        base = ws["local"].data_ptr()
+        main = torch.cuda.current_stream(self.tdev)
+        stream = main.cuda_stream or 1
+        if self.world == 1:
+            base = ws["local"].data_ptr()
+            self.index.search_device(d_queries.data_ptr(), batch, k, base, base + blk.off_dist, base + blk.off_counts,
+                                     ws["flags"].data_ptr(), stream)
+            return ws["local"]
+        if not pipelined:
+            base = ws["local"].data_ptr()
+            self.index.search_device(d_queries.data_ptr(), batch, k, base, base + blk.off_dist, base + blk.off_counts,
+                                     ws["flags"].data_ptr(), stream)
+            all_gather_blocks(ws["local"], ws["gathered"], self.group)
+            g, o = ws["gathered"].data_ptr(), ws["out"].data_ptr()
+            merge_results_device(self.device, g, g + blk.off_dist, g + blk.off_counts, self.world, batch, k,
+                                 o, o + blk.off_dist, o + blk.off_counts, stream, list_stride_bytes=blk.nbytes)
+            return ws["out"]
+        # ---- pipelined: double-buffered blocks, exchange + merge on a side stream
+        if "pipe" not in ws:
+            d = self.tdev
+            ws["pipe"] = {
+                "local": [torch.zeros(blk.nbytes, dtype=torch.uint8, device=d) for _ in range(2)],
+                "gathered": [torch.zeros((self.world, blk.nbytes), dtype=torch.uint8, device=d) for _ in range(2)],
+                "out": [torch.zeros(blk.nbytes, dtype=torch.uint8, device=d) for _ in range(2)],
+                "searched": [torch.cuda.Event() for _ in range(2)],
+                "merged": [None, None],
+                "step": 0,
+            }
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.tdev)
+        pp = ws["pipe"]
+        p = pp["step"] & 1
+        pp["step"] += 1
+        if pp["merged"][p] is not None:  # the side stream must be done with these buffers (two batches ago)
+            main.wait_event(pp["merged"][p])
+        base = pp["local"][p].data_ptr()
         self.index.search_device(d_queries.data_ptr(), batch, k, base, base + blk.off_dist, base + blk.off_counts,
                                  ws["flags"].data_ptr(), stream)
-        if self.world == 1:
-            return ws["local"]
-        all_gather_blocks(ws["local"], ws["gathered"], self.group)
-        g, o = ws["gathered"].data_ptr(), ws["out"].data_ptr()
-        merge_results_device(self.device, g, g + blk.off_dist, g + blk.off_counts, self.world, batch, k,
-                             o, o + blk.off_dist, o + blk.off_counts, stream, list_stride_bytes=blk.nbytes)
-        return ws["out"]
+        pp["searched"][p].record(main)
+        side = self._side
+        side.wait_event(pp["searched"][p])
+        with torch.cuda.stream(side):
+            all_gather_blocks(pp["local"][p], pp["gathered"][p], self.group)
+            g, o = pp["gathered"][p].data_ptr(), pp["out"][p].data_ptr()
+            merge_results_device(self.device, g, g + blk.off_dist, g + blk.off_counts, self.world, batch, k,
+                                 o, o + blk.off_dist, o + blk.off_counts, side.cuda_stream, list_stride_bytes=blk.nbytes)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        pp["merged"][p] = ev
+        self._last_merged = ev
+        return pp["out"][p]
+
+    def wait_results(self):
+        """Make the current stream wait for the last pipelined batch's exchange + merge."""
+        if self._last_merged is not None:
+            torch.cuda.current_stream(self.tdev).wait_event(self._last_merged)
 
     def search(self, queries: np.ndarray, k: int):
         """Host queries in, host results out (every rank gets the full merged answer)."""

@@ -109,3 +109,59 @@ def test_single_process_multi_index_synthetic_and_duplicates(dawn, oracle):
         m.add_batch(labels, rows)
         r = m.search(base[0], 10)
         assert list(r.labels) == list(range(1, 11))
+
+
+PIPE_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["DAWN_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from dawnsearch_b200.sharded import ShardedIndex, shard_range
+from oracle import oracle as O
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+torch.cuda.set_device(local)
+SEED, rows = 0xDA5EA2C4, 400_000
+first, n = shard_range(rank, world, rows)
+sh = ShardedIndex(local, n)
+sh.index.add_synthetic(SEED, first, n)
+stored = O.synth_rows_f16(SEED, 0, rows) if rank == 0 else None
+ok = True
+k, batch, steps = 10, 32, 5
+qs = [O.make_queries(SEED, 90 + i, batch, rows) for i in range(steps)]
+dq = [torch.from_numpy(q).cuda() for q in qs]
+outs = []
+for i in range(steps):  # back-to-back pipelined batches; copy each result out as soon as it is complete
+    blk = sh.search_device(dq[i], k, pipelined=True)
+    sh.wait_results()
+    outs.append(blk.clone())
+torch.cuda.synchronize()
+if rank == 0:
+    from dawnsearch_b200.sharded import ResultBlock
+    rb = ResultBlock(batch, k)
+    for i in range(steps):
+        L, D, Cn = rb.views(outs[i].cpu())
+        wl, wd, wc, _ = O.cpu_scan_f16(stored, None, qs[i], k)
+        same = (L.numpy().astype(np.uint64) == wl).all() and (D.numpy().view(np.uint32) == wd.view(np.uint32)).all()
+        print("step", i, "ok" if same else "MISMATCH", flush=True)
+        ok &= bool(same)
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.broadcast(flag, 0)
+sh.close()
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)
+'''
+
+
+def test_two_gpu_pipelined_exchange_matches_oracle(tmp_path):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    script = tmp_path / "pipe_worker.py"
+    script.write_text(PIPE_WORKER)
+    env = dict(os.environ, DAWN_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" ok") == 5, r.stdout
