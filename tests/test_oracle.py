@@ -257,3 +257,36 @@ def test_hnsw_restatement_behaves_like_an_ann_index(oracle):
     assert recalls[0] <= recalls[1] <= recalls[2] and recalls[2] > 0.99
     l, d = h.search(rows[7], 20)  # self query (src/net/web.rs:339)
     assert l[0] == 8 and abs(d[0]) < 1e-3
+
+
+# ---- property tests (hypothesis): C oracle == numpy restatement == threaded scan on arbitrary small inputs
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(1, 300), k=st.integers(1, 120), seed=st.integers(0, 2 ** 32 - 1), dup=st.booleans(),
+       label_mode=st.sampled_from(["rowid", "huge", "repeated"]))
+def test_property_oracles_agree(oracle, n, k, seed, dup, label_mode):
+    rng = np.random.default_rng(seed)
+    rows = oracle.np_synth_rows_f32(seed, 0, n)
+    if dup and n > 2:
+        rows[rng.integers(0, n, size=n // 2)] = rows[rng.integers(0, n)]
+    if label_mode == "rowid":
+        labels = np.arange(1, n + 1, dtype=np.uint64)
+    elif label_mode == "huge":
+        labels = rng.integers(1, 2 ** 63, size=n, dtype=np.int64).astype(np.uint64)
+    else:
+        labels = rng.integers(1, max(2, n // 2), size=n, dtype=np.int64).astype(np.uint64)
+    stored = rows.astype(np.float16)
+    q = oracle.make_queries(seed, seed ^ 0xABCD, 1, n)[0]
+    l1, d1 = oracle.search_f16(stored, labels, q, k)
+    l2, d2 = oracle.np_search(stored.astype(np.float32), labels, q, k)
+    lo, do, cnt, _ = oracle.cpu_scan_f16(stored, labels, q[None, :], k, threads=3)
+    assert len(l1) == min(k, n)
+    assert (l1 == l2).all() and (bits(d1) == bits(d2)).all()
+    assert cnt[0] == len(l1) and (lo[0, : cnt[0]] == l1).all() and (bits(do[0, : cnt[0]]) == bits(d1)).all()
+    assert (np.diff(d1) >= 0).all()
+    # ties are ordered by ascending label
+    for i in range(len(l1) - 1):
+        if bits(d1[i:i + 1])[0] == bits(d1[i + 1:i + 2])[0]:
+            assert l1[i] <= l1[i + 1]
