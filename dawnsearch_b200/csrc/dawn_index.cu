@@ -102,6 +102,12 @@ struct dawn_index {
     int64_t gemm_chunk_tiles = 0;  // 0 auto
     int64_t gemm_sequential_tiles = 0;
 
+    // The search workspace (partials, counters, K3 logs) is shared by all searches on this handle:
+    // a search enqueued on another stream than the previous one first waits for it.
+    cudaEvent_t ws_done = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_used = false;
+
     bool profiling = false;
     std::vector<EventPair> pending;
     std::vector<EventPair> free_events;
@@ -290,9 +296,26 @@ int ensure_query_ws(dawn_index *idx, size_t batch, size_t k) {
 }
 
 // Enqueue the whole search for `batch` device-resident queries on stream `s`.
+int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, size_t k, int kprime,
+                        uint64_t *d_labels_out, float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags,
+                        cudaStream_t s, bool scan_only);
+
 int search_enqueue(dawn_index *idx, const float *d_queries, size_t batch, size_t k, int kprime,
                    uint64_t *d_labels_out, float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags,
                    cudaStream_t s, bool scan_only = false) {
+    if (idx->ws_used && idx->ws_stream != s) CK(idx, cudaStreamWaitEvent(s, idx->ws_done, 0));
+    int rc = search_enqueue_impl(idx, d_queries, batch, k, kprime, d_labels_out, d_dist_out, d_counts, d_flags, s, scan_only);
+    if (rc == DAWN_OK) {
+        CK(idx, cudaEventRecord(idx->ws_done, s));
+        idx->ws_stream = s;
+        idx->ws_used = true;
+    }
+    return rc;
+}
+
+int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, size_t k, int kprime,
+                        uint64_t *d_labels_out, float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags,
+                        cudaStream_t s, bool scan_only) {
     const int grid = idx->sm_count;
     if (idx->scalar == DAWN_SCALAR_I8) {
         // K4: int8 storage -> streaming dp4a scan, 1 or 2 queries per pass, exact f32 re-score
@@ -574,6 +597,7 @@ int dawn_index_create(const dawn_options *opts, dawn_index **out) {
         idx->h_stage_labels = idx->h_labels_buf[0];
         idx->d_stage = idx->d_stage_buf[0];
         if ((e = cudaMallocHost(&idx->h_word, 64)) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&idx->ws_done, cudaEventDisableTiming)) != cudaSuccess) break;
     } while (0);
     if (e != cudaSuccess) {
         rc = fail(DAWN_ERR_CUDA, "index setup failed: %s", cudaGetErrorString(e));
@@ -623,6 +647,7 @@ void dawn_index_free(dawn_index *idx) {
     cudaFree(idx->d_counters);
     cudaFree(idx->d_gemm_ws);
     cudaFreeHost(idx->h_word);
+    if (idx->ws_done) cudaEventDestroy(idx->ws_done);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     cudaGetLastError();
     delete idx;
