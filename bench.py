@@ -319,6 +319,7 @@ def run_ours(args):
     # ---- latency configuration: one query per step -----------------------------------------
     batch1 = None
     if args.latency_steps > 0 and B != 1:
+        time.sleep(1.0)  # the throughput run leaves the chip on its power cap; latency is a separate workload
         q1_host = [pool_host[0][i:i + 1] for i in range(min(B, 16))]
         q1_dev = [pool_dev[0][i:i + 1] for i in range(min(B, 16))]
         t_ms, s_ms, p1, _ = timed_device(q1_dev, k, args.latency_steps, 20)

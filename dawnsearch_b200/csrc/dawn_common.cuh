@@ -122,6 +122,9 @@ struct FinalizeLaunch {
     int scalar;             // 0 = fp16 rows (corpus is __half*), 1 = blocked int8 arena (corpus is uint8_t*)
     const float *eps_q;     // optional per-query eps (GEMM path: depends on the query's fp16 rounding)
     const uint32_t *overflow;  // optional per-query "candidate log overflowed" flags -> not certified
+    uint32_t *counters;     // optional: [n_counters] words (status word first) that CTA 0 zeroes for the next search
+    int n_counters;
+    uint32_t *status_out;   // optional: receives counters[0] (scan status) before the reset
 };
 // K5+K6: merge per-CTA lists, re-score candidates in the reference's order of summation
 // (src/search/vector.rs:128-134), final order and 1 - score.

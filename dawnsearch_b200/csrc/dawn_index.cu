@@ -80,11 +80,11 @@ struct dawn_index {
     // search workspace
     size_t q_cap = 0;  // queries
     float *d_queries = nullptr, *h_queries = nullptr;
-    uint64_t *d_labels_out = nullptr, *h_labels_out = nullptr;
-    float *d_dist_out = nullptr, *h_dist_out = nullptr;
-    uint32_t *d_counts = nullptr, *h_counts = nullptr;
-    uint32_t *d_flags = nullptr, *h_flags = nullptr;
-    size_t out_cap = 0;  // entries of labels/dist out
+    // results of the host API: ONE packed block (labels | distances | counts | flags | status) so that a
+    // search costs a single D2H copy
+    uint8_t *d_result = nullptr, *h_result = nullptr;
+    size_t result_cap = 0;
+    bool counters_clean = false;  // finalize leaves the chunk counters / status word zeroed for the next search
     Cand *d_partials = nullptr;
     size_t partials_cap = 0;
     uint32_t *d_counters = nullptr;  // one chunk counter per scan pass, + status word at [0]
@@ -261,61 +261,84 @@ int choose_kprime(size_t k) {
     return kp > kMaxCand ? kMaxCand : kp;
 }
 
+struct ResultView {
+    uint64_t *labels;
+    float *dist;
+    uint32_t *counts, *flags, *status;
+    size_t bytes;
+};
+inline ResultView result_view(uint8_t *base, size_t batch, size_t k) {
+    ResultView v;
+    v.labels = reinterpret_cast<uint64_t *>(base);
+    v.dist = reinterpret_cast<float *>(base + batch * k * 8);
+    v.counts = reinterpret_cast<uint32_t *>(base + batch * k * 12);
+    v.flags = v.counts + batch;
+    v.status = v.flags + batch;
+    v.bytes = batch * k * 12 + batch * 8 + 16;
+    return v;
+}
+
 int ensure_query_ws(dawn_index *idx, size_t batch, size_t k) {
     if (batch > idx->q_cap) {
         size_t cap = batch < 64 ? 64 : batch;
         if (idx->d_queries) cudaFree(idx->d_queries);
         if (idx->h_queries) cudaFreeHost(idx->h_queries);
-        if (idx->d_counts) cudaFree(idx->d_counts);
-        if (idx->h_counts) cudaFreeHost(idx->h_counts);
-        if (idx->d_flags) cudaFree(idx->d_flags);
-        if (idx->h_flags) cudaFreeHost(idx->h_flags);
         idx->q_cap = 0;
         CK(idx, cudaMalloc(&idx->d_queries, cap * kDim * sizeof(float)));
         CK(idx, cudaMallocHost(&idx->h_queries, cap * kDim * sizeof(float)));
-        CK(idx, cudaMalloc(&idx->d_counts, cap * sizeof(uint32_t)));
-        CK(idx, cudaMallocHost(&idx->h_counts, cap * sizeof(uint32_t)));
-        CK(idx, cudaMalloc(&idx->d_flags, cap * sizeof(uint32_t)));
-        CK(idx, cudaMallocHost(&idx->h_flags, cap * sizeof(uint32_t)));
         idx->q_cap = cap;
     }
-    if (batch * k > idx->out_cap) {
-        size_t cap = batch * k < 4096 ? 4096 : batch * k;
-        if (idx->d_labels_out) cudaFree(idx->d_labels_out);
-        if (idx->h_labels_out) cudaFreeHost(idx->h_labels_out);
-        if (idx->d_dist_out) cudaFree(idx->d_dist_out);
-        if (idx->h_dist_out) cudaFreeHost(idx->h_dist_out);
-        idx->out_cap = 0;
-        CK(idx, cudaMalloc(&idx->d_labels_out, cap * sizeof(uint64_t)));
-        CK(idx, cudaMallocHost(&idx->h_labels_out, cap * sizeof(uint64_t)));
-        CK(idx, cudaMalloc(&idx->d_dist_out, cap * sizeof(float)));
-        CK(idx, cudaMallocHost(&idx->h_dist_out, cap * sizeof(float)));
-        idx->out_cap = cap;
+    const size_t need = batch * (k ? k : 1) * 12 + batch * 8 + 16;
+    if (need > idx->result_cap) {
+        size_t cap = need < 65536 ? 65536 : need;
+        if (idx->d_result) cudaFree(idx->d_result);
+        if (idx->h_result) cudaFreeHost(idx->h_result);
+        idx->result_cap = 0;
+        CK(idx, cudaMalloc(&idx->d_result, cap));
+        CK(idx, cudaMallocHost(&idx->h_result, cap));
+        idx->result_cap = cap;
     }
+    return DAWN_OK;
+}
+
+// Zero the chunk counters / status word unless the previous search's finalize already did.
+int prepare_counters(dawn_index *idx, size_t need, cudaStream_t s) {
+    if (need > idx->counters_cap) {
+        size_t cap = need < 1024 ? 1024 : need;
+        if (idx->d_counters) cudaFree(idx->d_counters);
+        idx->counters_cap = 0;
+        CK(idx, cudaMalloc(&idx->d_counters, cap * sizeof(uint32_t)));
+        idx->counters_cap = cap;
+        idx->counters_clean = false;
+    }
+    if (!idx->counters_clean) CK(idx, cudaMemsetAsync(idx->d_counters, 0, idx->counters_cap * sizeof(uint32_t), s));
+    idx->counters_clean = false;  // dirty until this search's finalize has been enqueued
     return DAWN_OK;
 }
 
 // Enqueue the whole search for `batch` device-resident queries on stream `s`.
 int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, size_t k, int kprime,
                         uint64_t *d_labels_out, float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags,
-                        cudaStream_t s, bool scan_only);
+                        cudaStream_t s, bool scan_only, uint32_t *d_status_out);
 
 int search_enqueue(dawn_index *idx, const float *d_queries, size_t batch, size_t k, int kprime,
                    uint64_t *d_labels_out, float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags,
-                   cudaStream_t s, bool scan_only = false) {
+                   cudaStream_t s, bool scan_only = false, uint32_t *d_status_out = nullptr) {
     if (idx->ws_used && idx->ws_stream != s) CK(idx, cudaStreamWaitEvent(s, idx->ws_done, 0));
-    int rc = search_enqueue_impl(idx, d_queries, batch, k, kprime, d_labels_out, d_dist_out, d_counts, d_flags, s, scan_only);
+    int rc = search_enqueue_impl(idx, d_queries, batch, k, kprime, d_labels_out, d_dist_out, d_counts, d_flags, s, scan_only,
+                                 d_status_out);
     if (rc == DAWN_OK) {
         CK(idx, cudaEventRecord(idx->ws_done, s));
         idx->ws_stream = s;
         idx->ws_used = true;
+        idx->counters_clean = true;  // every path ends with a finalize that zeroes the counters it used
     }
     return rc;
 }
 
 int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, size_t k, int kprime,
                         uint64_t *d_labels_out, float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags,
-                        cudaStream_t s, bool scan_only) {
+                        cudaStream_t s, bool scan_only, uint32_t *d_status_out) {
     const int grid = idx->sm_count;
     if (idx->scalar == DAWN_SCALAR_I8) {
         // K4: int8 storage -> streaming dp4a scan, 1 or 2 queries per pass, exact f32 re-score
@@ -336,14 +359,10 @@ int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, s
             idx->partials_cap = need_partials;
         }
         const size_t need_counters = batch + 1;
-        if (need_counters > idx->counters_cap) {
-            size_t cap = need_counters < 1024 ? 1024 : need_counters;
-            if (idx->d_counters) cudaFree(idx->d_counters);
-            idx->counters_cap = 0;
-            CK(idx, cudaMalloc(&idx->d_counters, cap * sizeof(uint32_t)));
-            idx->counters_cap = cap;
+        {
+            int prc = prepare_counters(idx, need_counters, s);
+            if (prc) return prc;
         }
-        CK(idx, cudaMemsetAsync(idx->d_counters, 0, need_counters * sizeof(uint32_t), s));
         CK(idx, launch_prep_queries_i8(d_queries, (int)batch, d_iq, d_eps, s));
         idx->prof.kernel_launches++;
         size_t done = 0, pass = 0;
@@ -385,6 +404,9 @@ int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, s
         fl.scalar = 1;
         fl.eps_q = d_eps;
         fl.overflow = nullptr;
+        fl.counters = idx->d_counters;
+        fl.n_counters = (int)need_counters;
+        fl.status_out = d_status_out;
         EventPair ev;
         bool timed = begin_event(idx, 1, s, &ev);
         CK(idx, launch_finalize(fl, s));
@@ -415,11 +437,10 @@ int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, s
             CK(idx, cudaMalloc(&idx->d_partials, qp * kprime * sizeof(Cand)));
             idx->partials_cap = qp * kprime;
         }
-        if (idx->counters_cap < 1) {
-            CK(idx, cudaMalloc(&idx->d_counters, 1024 * sizeof(uint32_t)));
-            idx->counters_cap = 1024;
+        {
+            int prc = prepare_counters(idx, 1, s);
+            if (prc) return prc;
         }
-        CK(idx, cudaMemsetAsync(idx->d_counters, 0, sizeof(uint32_t), s));
         GemmSearch gs;
         gs.corpus = idx->corpus;
         gs.labels = idx->labels;
@@ -462,6 +483,9 @@ int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, s
         fl.scalar = 0;
         fl.eps_q = eps_q;
         fl.overflow = overflow;
+        fl.counters = idx->d_counters;
+        fl.n_counters = 1;
+        fl.status_out = d_status_out;
         EventPair evf;
         bool timedf = begin_event(idx, 1, s, &evf);
         CK(idx, launch_finalize(fl, s));
@@ -480,14 +504,10 @@ int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, s
         idx->partials_cap = need_partials;
     }
     const size_t need_counters = batch + 1;
-    if (need_counters > idx->counters_cap) {
-        size_t cap = need_counters < 1024 ? 1024 : need_counters;
-        if (idx->d_counters) cudaFree(idx->d_counters);
-        idx->counters_cap = 0;
-        CK(idx, cudaMalloc(&idx->d_counters, cap * sizeof(uint32_t)));
-        idx->counters_cap = cap;
+    {
+        int prc = prepare_counters(idx, need_counters, s);
+        if (prc) return prc;
     }
-    CK(idx, cudaMemsetAsync(idx->d_counters, 0, need_counters * sizeof(uint32_t), s));
 
     size_t done = 0;
     size_t pass = 0;
@@ -531,6 +551,9 @@ int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, s
     fl.scalar = 0;
     fl.eps_q = nullptr;
     fl.overflow = nullptr;
+    fl.counters = idx->d_counters;
+    fl.n_counters = (int)need_counters;
+    fl.status_out = d_status_out;
     EventPair ev;
     bool timed = begin_event(idx, 1, s, &ev);
     CK(idx, launch_finalize(fl, s));
@@ -635,14 +658,8 @@ void dawn_index_free(dawn_index *idx) {
     }
     cudaFree(idx->d_queries);
     cudaFreeHost(idx->h_queries);
-    cudaFree(idx->d_labels_out);
-    cudaFreeHost(idx->h_labels_out);
-    cudaFree(idx->d_dist_out);
-    cudaFreeHost(idx->h_dist_out);
-    cudaFree(idx->d_counts);
-    cudaFreeHost(idx->h_counts);
-    cudaFree(idx->d_flags);
-    cudaFreeHost(idx->h_flags);
+    cudaFree(idx->d_result);
+    cudaFreeHost(idx->h_result);
     cudaFree(idx->d_partials);
     cudaFree(idx->d_counters);
     cudaFree(idx->d_gemm_ws);
@@ -742,43 +759,38 @@ int dawn_index_search_batch(dawn_index *idx, const float *queries, size_t batch,
     CK(idx, cudaMemcpyAsync(idx->d_queries, idx->h_queries, batch * kDim * sizeof(float), cudaMemcpyHostToDevice, s));
     int kprime = choose_kprime(k);
     const uint64_t gemm_before = idx->prof.gemm_batches;
-    rc = search_enqueue(idx, idx->d_queries, batch, k, kprime, idx->d_labels_out, idx->d_dist_out, idx->d_counts,
-                        idx->d_flags, s);
+    ResultView dv = result_view(idx->d_result, batch, k), hv = result_view(idx->h_result, batch, k);
+    rc = search_enqueue(idx, idx->d_queries, batch, k, kprime, dv.labels, dv.dist, dv.counts, dv.flags, s, false, dv.status);
     if (rc) return rc;
-    CK(idx, cudaMemcpyAsync(idx->h_labels_out, idx->d_labels_out, batch * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CK(idx, cudaMemcpyAsync(idx->h_dist_out, idx->d_dist_out, batch * k * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CK(idx, cudaMemcpyAsync(idx->h_counts, idx->d_counts, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CK(idx, cudaMemcpyAsync(idx->h_flags, idx->d_flags, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CK(idx, cudaMemcpyAsync(idx->h_word, idx->d_counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(idx, cudaMemcpyAsync(idx->h_result, idx->d_result, dv.bytes, cudaMemcpyDeviceToHost, s));  // the one D2H
     CK(idx, cudaStreamSynchronize(s));
-    if (idx->h_word[0] != 0) return fail(DAWN_ERR_INTERNAL, "scan kernel reported status 0x%x", idx->h_word[0]);
-    memcpy(labels_out, idx->h_labels_out, batch * k * sizeof(uint64_t));
-    memcpy(distances_out, idx->h_dist_out, batch * k * sizeof(float));
-    for (size_t b = 0; b < batch; b++) counts_out[b] = idx->h_counts[b];
+    if (hv.status[0] != 0) return fail(DAWN_ERR_INTERNAL, "scan kernel reported status 0x%x", hv.status[0]);
+    memcpy(labels_out, hv.labels, batch * k * sizeof(uint64_t));
+    memcpy(distances_out, hv.dist, batch * k * sizeof(float));
+    for (size_t b = 0; b < batch; b++) counts_out[b] = hv.counts[b];
 
-    // Exactness certificate not met (near-ties deeper than the slack): re-run those queries
-    // with the longest candidate list.
+    // Exactness certificate not met (near-ties deeper than the slack, or a tensor-core-path log
+    // overflow): re-run those queries through the f32 scan with the longest candidate list.
     const bool can_escalate = kprime < kMaxCand || idx->prof.gemm_batches > gemm_before;
-    if (can_escalate) {
-        for (size_t b = 0; b < batch; b++) {
-            if (idx->h_flags[b] & 1u) continue;
-            idx->prof.escalations++;
-            rc = search_enqueue(idx, idx->d_queries + b * kDim, 1, k, kMaxCand, idx->d_labels_out, idx->d_dist_out,
-                                idx->d_counts, idx->d_flags, s, /*scan_only=*/true);
-            if (rc) return rc;
-            CK(idx, cudaMemcpyAsync(idx->h_labels_out, idx->d_labels_out, k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-            CK(idx, cudaMemcpyAsync(idx->h_dist_out, idx->d_dist_out, k * sizeof(float), cudaMemcpyDeviceToHost, s));
-            CK(idx, cudaMemcpyAsync(idx->h_counts, idx->d_counts, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-            CK(idx, cudaMemcpyAsync(idx->h_word + 1, idx->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-            CK(idx, cudaStreamSynchronize(s));
-            memcpy(labels_out + b * k, idx->h_labels_out, k * sizeof(uint64_t));
-            memcpy(distances_out + b * k, idx->h_dist_out, k * sizeof(float));
-            counts_out[b] = idx->h_counts[0];
-            if (!(idx->h_word[1] & 1u)) idx->prof.uncertified++;
-        }
-    } else {
-        for (size_t b = 0; b < batch; b++)
-            if (!(idx->h_flags[b] & 1u)) idx->prof.uncertified++;
+    std::vector<size_t> redo;
+    for (size_t b = 0; b < batch; b++)
+        if (!(hv.flags[b] & 1u)) redo.push_back(b);
+    if (!can_escalate) {
+        idx->prof.uncertified += redo.size();
+        return DAWN_OK;
+    }
+    for (size_t b : redo) {
+        idx->prof.escalations++;
+        ResultView d1 = result_view(idx->d_result, 1, k), h1 = result_view(idx->h_result, 1, k);
+        rc = search_enqueue(idx, idx->d_queries + b * kDim, 1, k, kMaxCand, d1.labels, d1.dist, d1.counts, d1.flags, s,
+                            /*scan_only=*/true, d1.status);
+        if (rc) return rc;
+        CK(idx, cudaMemcpyAsync(idx->h_result, idx->d_result, d1.bytes, cudaMemcpyDeviceToHost, s));
+        CK(idx, cudaStreamSynchronize(s));
+        memcpy(labels_out + b * k, h1.labels, k * sizeof(uint64_t));
+        memcpy(distances_out + b * k, h1.dist, k * sizeof(float));
+        counts_out[b] = h1.counts[0];
+        if (!(h1.flags[0] & 1u)) idx->prof.uncertified++;
     }
     return DAWN_OK;
 }
@@ -825,13 +837,15 @@ int dawn_index_get(dawn_index *idx, uint64_t label, float *vector384_out) {
     rc = ensure_query_ws(idx, 1, 1);
     if (rc) return rc;
     cudaStream_t s = idx->stream;
-    CK(idx, launch_find_label(idx->labels, idx->size, label, idx->d_counts, s));
+    uint32_t *d_row = reinterpret_cast<uint32_t *>(idx->d_result);
+    uint32_t *h_row = reinterpret_cast<uint32_t *>(idx->h_result);
+    CK(idx, launch_find_label(idx->labels, idx->size, label, d_row, s));
     idx->prof.kernel_launches++;
-    CK(idx, cudaMemcpyAsync(idx->h_counts, idx->d_counts, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(idx, cudaMemcpyAsync(h_row, d_row, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CK(idx, cudaStreamSynchronize(s));
-    if (idx->h_counts[0] == kNoRow) return fail(DAWN_ERR_INVALID, "label %llu not found", (unsigned long long)label);
-    if (idx->scalar == DAWN_SCALAR_I8) CK(idx, launch_gather_f32_i8(arena_i8(idx), idx->d_counts, 1, idx->d_queries, s));
-    else CK(idx, launch_gather_f32(idx->corpus, idx->d_counts, 1, idx->d_queries, s));
+    if (h_row[0] == kNoRow) return fail(DAWN_ERR_INVALID, "label %llu not found", (unsigned long long)label);
+    if (idx->scalar == DAWN_SCALAR_I8) CK(idx, launch_gather_f32_i8(arena_i8(idx), d_row, 1, idx->d_queries, s));
+    else CK(idx, launch_gather_f32(idx->corpus, d_row, 1, idx->d_queries, s));
     idx->prof.kernel_launches++;
     CK(idx, cudaMemcpyAsync(idx->h_queries, idx->d_queries, kDim * sizeof(float), cudaMemcpyDeviceToHost, s));
     CK(idx, cudaStreamSynchronize(s));

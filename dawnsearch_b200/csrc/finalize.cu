@@ -32,7 +32,15 @@ struct FinSmem {
     float kth_dist;
     alignas(16) Cand s[1];  // kFinCapEntries entries when merging, kp entries for a single list
 };
-inline size_t fin_smem_bytes(int entries) { return sizeof(FinSmem) + (size_t)(entries - 1) * sizeof(Cand); }
+constexpr int kRowStrideF16 = kRowBytesF16 + 16;  // staged candidate rows: +16 B so that thread-per-row reads are conflict free
+constexpr int kRowStrideI8 = kDim + 16;
+// header + candidate area + staged rows of the kp survivors
+// (rows are staged only when merging per-CTA lists: one CTA per query on an otherwise idle GPU; with one
+// pre-merged list per query there are as many CTAs as queries and occupancy matters more)
+inline size_t fin_smem_bytes(int entries, int kp, int scalar, bool stage_rows) {
+    return sizeof(FinSmem) + (size_t)(entries - 1) * sizeof(Cand) +
+           (stage_rows ? (size_t)kp * (scalar ? kRowStrideI8 : kRowStrideF16) : 0);
+}
 
 __device__ __forceinline__ bool dist_before(const Cand &a, const Cand &b) {
     if (a.score != b.score) return a.score < b.score;
@@ -84,7 +92,8 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
                 const Cand *__restrict__ partials, int n_lists, int kp, int k, float eps,
                 uint64_t *__restrict__ labels_out, float *__restrict__ distances_out,
                 uint32_t *__restrict__ counts_out, uint32_t *__restrict__ flags_out,
-                const float *__restrict__ eps_q, const uint32_t *__restrict__ overflow, int scalar) {
+                const float *__restrict__ eps_q, const uint32_t *__restrict__ overflow, int scalar,
+                uint32_t *__restrict__ counters, int n_counters, uint32_t *__restrict__ status_out) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FinSmem &sm = *reinterpret_cast<FinSmem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -114,18 +123,39 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
     }
     __syncthreads();
 
-    // ---- K6: exact re-score, one candidate per thread, sequential f32 mul + add
+    // ---- K6: exact re-score.  The survivors' rows are first staged in shared memory by the whole CTA
+    // (coalesced, one round trip to L2/HBM), then one thread per candidate adds the 384 products
+    // sequentially in f32 -- the reference's order (vector.rs:128-134).
+    const bool stage_rows = n_lists > 1;
+    const int entries = n_lists == 1 ? kp : kFinCapEntries;
+    uint8_t *rows_sm = reinterpret_cast<uint8_t *>(sm.s + entries);
+    const int stride = scalar ? kRowStrideI8 : kRowStrideF16;
+    const int units = (scalar ? kDim : kRowBytesF16) / 16;  // 16-byte pieces per row
+    for (int i = tid; stage_rows && i < kp * units; i += nthr) {
+        const int c = i / units, j = i % units;
+        const uint32_t row = sm.s[c].row;
+        if (row != kNoRow) {
+            const uint8_t *src = scalar ? reinterpret_cast<const uint8_t *>(corpus) + i8_row_offset(row)
+                                        : reinterpret_cast<const uint8_t *>(corpus + (size_t)row * kDim);
+            *reinterpret_cast<uint4 *>(rows_sm + c * stride + j * 16) = __ldg(reinterpret_cast<const uint4 *>(src) + j);
+        }
+    }
+    __syncthreads();
     Cand mine = empty_cand();
     if (tid < kp) {
         mine = sm.s[tid];
         sm.scan_score[tid] = mine.row != kNoRow ? mine.score : __int_as_float(0x7f800000);
         if (mine.row != kNoRow) {
             float acc = 0.0f;
+            const uint4 *rp = stage_rows
+                                  ? reinterpret_cast<const uint4 *>(rows_sm + tid * stride)
+                                  : reinterpret_cast<const uint4 *>(
+                                        scalar ? reinterpret_cast<const uint8_t *>(corpus) + i8_row_offset(mine.row)
+                                               : reinterpret_cast<const uint8_t *>(corpus + (size_t)mine.row * kDim));
             if (scalar == 0) {
-                const uint4 *rp = reinterpret_cast<const uint4 *>(corpus + (size_t)mine.row * kDim);
 #pragma unroll 4
                 for (int c = 0; c < kDim / 8; c++) {
-                    const uint4 u = __ldg(rp + c);
+                    const uint4 u = rp[c];
                     const __half2 *h = reinterpret_cast<const __half2 *>(&u);
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
@@ -136,16 +166,14 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
                 }
             } else {
                 // int8 rows: score = scale * sum q[i]*f32(x[i]) (oracle/dawn_oracle.c:dawn_oracle_search_i8)
-                const uint8_t *arena = reinterpret_cast<const uint8_t *>(corpus);
-                const uint4 *rp = reinterpret_cast<const uint4 *>(arena + i8_row_offset(mine.row));
 #pragma unroll 2
                 for (int c = 0; c < kDim / 16; c++) {
-                    const uint4 u = __ldg(rp + c);
-                    const int8_t *b = reinterpret_cast<const int8_t *>(&u);
+                    const uint4 u = rp[c];
+                    const int8_t *b8 = reinterpret_cast<const int8_t *>(&u);
 #pragma unroll
-                    for (int j = 0; j < 16; j++) acc = __fadd_rn(acc, __fmul_rn(sm.q[c * 16 + j], (float)b[j]));
+                    for (int j = 0; j < 16; j++) acc = __fadd_rn(acc, __fmul_rn(sm.q[c * 16 + j], (float)b8[j]));
                 }
-                acc = __fmul_rn(*reinterpret_cast<const float *>(arena + i8_scale_offset(mine.row)), acc);
+                acc = __fmul_rn(*reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(corpus) + i8_scale_offset(mine.row)), acc);
             }
             mine.score = __fsub_rn(1.0f, acc);  // distance, vector.rs:133
         }
@@ -194,6 +222,12 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
         if (overflow && overflow[qi]) certified = false;  // candidates were lost: cannot certify
         flags_out[qi] = certified ? 1u : 0u;
     }
+    // the last kernel of a search leaves the chunk counters / status word clean for the next one
+    if (blockIdx.x == 0 && counters) {
+        if (tid == 0 && status_out) *status_out = counters[0];
+        __syncthreads();
+        for (int i = tid; i < n_counters; i += nthr) counters[i] = 0u;
+    }
 }
 
 }  // namespace
@@ -204,16 +238,16 @@ cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s) {
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const size_t smem = fin_smem_bytes(p.n_lists == 1 ? p.kprime : kFinCapEntries);
+    const size_t smem = fin_smem_bytes(p.n_lists == 1 ? p.kprime : kFinCapEntries, p.kprime, p.scalar, p.n_lists > 1);
     if (dev < 64 && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)fin_smem_bytes(kFinCapEntries));
+                                             (int)fin_smem_bytes(kFinCapEntries, kMaxCand, 0, true));
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    finalize_kernel<<<p.nq, p.n_lists == 1 ? kFinThreadsSingle : kFinThreads, smem, s>>>(p.corpus, p.queries, p.partials, p.n_lists,
-                                                   p.kprime, p.k, p.eps, p.labels_out, p.distances_out,
-                                                   p.counts_out, p.flags_out, p.eps_q, p.overflow, p.scalar);
+    finalize_kernel<<<p.nq, p.n_lists == 1 ? kFinThreadsSingle : kFinThreads, smem, s>>>(
+        p.corpus, p.queries, p.partials, p.n_lists, p.kprime, p.k, p.eps, p.labels_out, p.distances_out, p.counts_out,
+        p.flags_out, p.eps_q, p.overflow, p.scalar, p.counters, p.n_counters, p.status_out);
     return cudaGetLastError();
 }
 
