@@ -30,6 +30,8 @@ struct FinSmem {
     float scan_score[kMaxCand];
     uint32_t n_valid;
     float kth_dist;
+    uint32_t n_surv;
+    float bound;
     alignas(16) Cand s[1];  // kFinCapEntries entries when merging, kp entries for a single list
 };
 constexpr int kRowStrideF16 = kRowBytesF16 + 16;  // staged candidate rows: +16 B so that thread-per-row reads are conflict free
@@ -87,6 +89,60 @@ __device__ void merge_lists(Cand *S, int n_lists, int kp, int tid) {
     }
 }
 
+// Fast K5 for many short lists.  The kp-th best of the lists' first ceil(kp/n_lists) entries is a lower
+// bound on the kp-th best score overall (those prefix entries are distinct candidates), so only
+// entries at or above it can be in the result: with 148 lists that is a few dozen out of thousands.
+// The survivors are ranked by counting under the full order and land sorted in S[0..kp).
+// Returns false (uniformly) when more than kSelSurvCap entries survive -- long runs of equal scores --
+// and the caller falls back to the tree merge.
+constexpr int kSelProbeMax = 512;
+constexpr int kSelSurvCap = 1024;
+__device__ bool select_lists(const Cand *__restrict__ lists, int n_lists, int kp, FinSmem &sm, int tid) {
+    Cand *S = sm.s;
+    Cand *surv = S + kSelSurvCap;                                   // [kSelSurvCap]
+    float *probe = reinterpret_cast<float *>(S + 2 * kSelSurvCap);  // [kSelProbeMax]
+    const int m = (kp + n_lists - 1) / n_lists;
+    const int n_probe = n_lists * m;
+    float mine = 0.0f;
+    if (tid < n_probe) {
+        mine = lists[(size_t)(tid / m) * kp + (tid % m)].score;
+        probe[tid] = mine;
+    }
+    if (tid == 0) sm.n_surv = 0u;
+    __syncthreads();
+    if (tid < n_probe) {
+        int rank = 0;
+        for (int j = 0; j < n_probe; j++) {
+            const float o = probe[j];
+            rank += (o > mine || (o == mine && j < tid)) ? 1 : 0;
+        }
+        if (rank == kp - 1) sm.bound = mine;
+    }
+    __syncthreads();
+    const float lb = sm.bound;
+    const int total = n_lists * kp;
+#pragma unroll 4
+    for (int i = tid; i < total; i += kFinThreads) {
+        const Cand c = lists[i];
+        if (c.row != kNoRow && c.score >= lb) {
+            const uint32_t slot = atomicAdd(&sm.n_surv, 1u);
+            if (slot < (uint32_t)kSelSurvCap) surv[slot] = c;
+        }
+    }
+    __syncthreads();
+    const int n_surv = (int)sm.n_surv;
+    if (n_surv > kSelSurvCap) return false;
+    if (tid < n_surv) {
+        const Cand me = surv[tid];
+        int rank = 0;
+        for (int j = 0; j < n_surv; j++) rank += cand_better(surv[j], me) ? 1 : 0;
+        if (rank < kp) S[rank] = me;
+    } else if (tid < kp) {
+        S[tid] = empty_cand();  // fewer than kp valid candidates in all lists together
+    }
+    return true;
+}
+
 __global__ void __launch_bounds__(kFinThreads, 1)
 finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ queries,
                 const Cand *__restrict__ partials, int n_lists, int kp, int k, float eps,
@@ -106,7 +162,10 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
     // ---- K5: streaming tree merge, cap_lists lists per round, list 0 is the running result
     if (n_lists == 1) {  // already one sorted list (tensor-core path): nothing to merge
         for (int i = tid; i < kp; i += nthr) sm.s[i] = lists[i];
+    } else if (n_lists * ((kp + n_lists - 1) / n_lists) <= kSelProbeMax && select_lists(lists, n_lists, kp, sm, tid)) {
+        // sorted result already in sm.s[0..kp)
     } else {             // requires blockDim.x == kFinThreads
+        __syncthreads();
         const int cap_lists = kFinCapEntries / kp;
         int next = 0;
         bool first = true;

@@ -27,6 +27,23 @@
 
 namespace dawn {
 
+#ifdef DAWN_SCAN_TRACE  // tools/scan_trace.cu: per-CTA timeline of the fp16 scan (never defined in the library build)
+__device__ unsigned long long g_scan_trace[148][12];
+#define SCAN_TRACE(slot)                                                          \
+    do {                                                                          \
+        unsigned long long t_;                                                    \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                    \
+        if (blockIdx.x < 148) g_scan_trace[blockIdx.x][slot] = t_;                \
+    } while (0)
+#define SCAN_TRACE_ADD(slot, v)                                                   \
+    do {                                                                          \
+        if (blockIdx.x < 148) g_scan_trace[blockIdx.x][slot] += (v);              \
+    } while (0)
+#else
+#define SCAN_TRACE(slot) do { } while (0)
+#define SCAN_TRACE_ADD(slot, v) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kConsumerWarps = 16;
@@ -108,6 +125,10 @@ struct ScanSmem {
 // Merge the append buffer into the sorted list, all 512 consumer threads, one query at a time.
 // Rank of an entry = number of entries that beat it; the list part is already sorted so only
 // the buffer needs counting.  Entries are unique under cand_better, so ranks are unique.
+// The streaming loop is stalled while this runs (the ring fills up and HBM goes idle), so the count
+// is spread over all threads -- 4 or 2 adjacent lanes share an entry when the entries are few -- and
+// its inner loop compares scores only (one LDS + two predicated adds per pair); the label / row
+// tie-break is a second pass run only by entries that actually met an equal score.
 template <int QT, class Smem>
 __device__ __forceinline__ void prune(Smem &sm, int kprime, int tid) {
 #pragma unroll 1
@@ -115,15 +136,19 @@ __device__ __forceinline__ void prune(Smem &sm, int kprime, int tid) {
         const int nb = min((int)((volatile uint32_t *)sm.cnt)[q], Smem::kBuf);
         const int len = (int)((volatile uint32_t *)sm.list_len)[q];
         const int total = len + nb;
-        const bool have = tid < total;
+        const int shift = total <= kConsumerThreads / 4 ? 2 : total <= kConsumerThreads / 2 ? 1 : 0;
+        const int ent = tid >> shift;          // entry handled by this thread
+        const int sub = tid & ((1 << shift) - 1);
+        const bool have = ent < total && nb > 0;
+        const bool from_buf = ent >= len;
         Cand e = empty_cand();
-        int rank = 0;
-        if (have && nb > 0) {
-            if (tid < len) {
-                e = sm.list[q][tid];
-                rank = tid;
+        int rank = 0, gt = 0, eq = 0;
+        if (have) {
+            if (!from_buf) {
+                e = sm.list[q][ent];
+                rank = ent;
             } else {
-                e = sm.buf[q][tid - len];
+                e = sm.buf[q][ent - len];
                 int lo = 0, hi = len;
                 while (lo < hi) {
                     int mid = (lo + hi) >> 1;
@@ -132,10 +157,27 @@ __device__ __forceinline__ void prune(Smem &sm, int kprime, int tid) {
                 }
                 rank = lo;
             }
-            for (int j = 0; j < nb; j++) rank += cand_better(sm.buf[q][j], e) ? 1 : 0;
+            const float es = e.score;
+#pragma unroll 8
+            for (int j = sub; j < nb; j += 1 << shift) {
+                const float s = sm.buf[q][j].score;
+                gt += s > es ? 1 : 0;
+                eq += s == es ? 1 : 0;
+            }
+        }
+        for (int o = 1; o < (1 << shift); o <<= 1) {
+            gt += __shfl_xor_sync(0xffffffffu, gt, o);
+            eq += __shfl_xor_sync(0xffffffffu, eq, o);
+        }
+        rank += gt;
+        if (have && sub == 0 && eq > (from_buf ? 1 : 0)) {  // equal scores: order them by (label, row)
+            for (int j = 0; j < nb; j++) {
+                const Cand o = sm.buf[q][j];
+                if (o.score == e.score && (o.label < e.label || (o.label == e.label && o.row < e.row))) rank++;
+            }
         }
         consumer_bar_sync();
-        if (have && nb > 0 && rank < kprime) sm.list[q][rank] = e;
+        if (have && sub == 0 && rank < kprime) sm.list[q][rank] = e;
         consumer_bar_sync();
         if (tid == 0) {
             int new_len = min(total, kprime);
@@ -160,6 +202,7 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
     const int lane = tid & 31;
 
     if (tid == 0) {
+        SCAN_TRACE(0);
         for (int s = 0; s < kStages; s++) {
             mbar_init(&sm.full_bar[s], 1);
             mbar_init(&sm.empty_bar[s], 1);
@@ -174,12 +217,14 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
         sm.thr[tid] = __int_as_float(0xff800000);
     }
     __syncthreads();
+    if (tid == 0) SCAN_TRACE(1);
 
     if (warp == kConsumerWarps) {
         // ===================== producer =====================
         if (lane != 0) return;
         uint32_t g = 0;
         uint32_t next = atomicAdd(chunk_counter, 1u);
+        SCAN_TRACE(2);
         while (true) {
             const uint32_t chunk = next;
             const uint64_t row0 = (uint64_t)chunk * kChunkRows;
@@ -199,6 +244,7 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
                          &sm.full_bar[slot]);
             }
         }
+        SCAN_TRACE(3);
         for (int w = 0; w < kConsumerWarps; w++, g++) {  // one end-of-stream stage per warp
             const uint32_t slot = g % kStages;
             mbar_wait(&sm.empty_bar[slot], ((g / kStages) & 1u) ^ 1u);
@@ -234,19 +280,29 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
 
     float thr = __int_as_float(0xff800000);
     uint32_t g = warp;
+    if (tid == 0) SCAN_TRACE(4);
     while (true) {
         // Join a prune if any query's buffer reached the high-water mark.
         {
             uint32_t c = lane < QT ? ((volatile uint32_t *)sm.cnt)[lane] : 0u;
             if (__any_sync(0xffffffffu, c >= (uint32_t)kHighWater)) {
+#ifdef DAWN_SCAN_TRACE
+                unsigned long long tp0, tp1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp0));
+#endif
                 consumer_bar_sync();
                 prune<QT>(sm, kprime, tid);
                 thr = ((volatile float *)sm.thr)[my_q];
+#ifdef DAWN_SCAN_TRACE
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp1));
+                if (tid == 0) { SCAN_TRACE_ADD(9, tp1 - tp0); SCAN_TRACE_ADD(10, 1ull); }
+#endif
                 continue;
             }
         }
         const uint32_t slot = g % kStages;
         mbar_wait(&sm.full_bar[slot], (g / kStages) & 1u);
+        if (tid == 0 && g == 0) SCAN_TRACE(5);
         const uint32_t row_base = sm.meta[slot].row_base;
         const uint32_t n_stage_rows = sm.meta[slot].n_rows;
         if (n_stage_rows == 0) break;
@@ -330,13 +386,16 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
 
     // End of this warp's stream: keep joining prunes until every consumer warp is done.
     __syncwarp();
+    if (tid == 0) SCAN_TRACE(6);
     if (lane == 0) atomicAdd(&sm.done_warps, 1u);
     while (true) {
         consumer_bar_sync();
         const uint32_t done = *((volatile uint32_t *)&sm.done_warps);
         prune<QT>(sm, kprime, tid);
+        if (tid == 0) SCAN_TRACE_ADD(11, 1ull);
         if (done == (uint32_t)kConsumerWarps) break;
     }
+    if (tid == 0) SCAN_TRACE(7);
 
     // One sorted, sentinel-padded list of k' candidates per query per CTA.
     for (int i = tid; i < QT * kprime; i += kConsumerThreads) {
@@ -345,6 +404,7 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
         partials[((size_t)q * gridDim.x + blockIdx.x) * kprime + j] = c;
     }
     if (tid == 0 && sm.overflow) atomicOr(status, 1u);  // cannot happen (static_assert above)
+    if (tid == 0) SCAN_TRACE(8);
 }
 
 

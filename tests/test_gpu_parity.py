@@ -137,6 +137,29 @@ def test_ties_break_on_lower_label(dawn, oracle):
             assert list(m.labels) == sorted(m.labels.tolist())  # all tied: ascending labels
 
 
+def test_long_runs_of_equal_scores_across_all_cta_lists(dawn, oracle):
+    """Tens of thousands of identical rows: every per-CTA list is full of tied candidates, so the
+    merge cannot prune by score and has to order thousands of ties by label."""
+    base = oracle.np_synth_rows_f32(6, 0, 2)
+    n_dup = 40_000
+    rows = np.concatenate([np.repeat(base[:1], n_dup, axis=0), oracle.np_synth_rows_f32(7, 0, 20_000)])
+    n = len(rows)
+    labels = perm_labels(oracle, n, salt=11)
+    stored = oracle.store_f16(rows)
+    with dawn.new_index(dawn.IndexOptions()) as idx:
+        idx.reserve(n)
+        idx.add_batch(labels, rows)
+        for k in (1, 20, 100):
+            m = idx.search(base[0], k)
+            assert_same((m.labels, m.distances), oracle.search_f16(stored, labels, base[0], k), f"k={k}")
+            assert list(m.labels) == sorted(labels[:n_dup].tolist())[:k]
+        qs = np.stack([base[0], base[1], base[0]])
+        gl, gd, cnt = idx.search_batch(qs, 10)
+        for i, q in enumerate(qs):
+            assert cnt[i] == 10
+            assert_same((gl[i], gd[i]), oracle.search_f16(stored, labels, q, 10), f"batch row {i}")
+
+
 def test_add_then_search_and_reserve_growth(dawn, oracle):
     """The reference's insert pattern: reserve(size+1024) when full, then add one vector
     (search_provider.rs:280-284); every add is visible to the next search."""
