@@ -100,6 +100,7 @@ struct ScanLaunch {
     uint32_t *chunk_counter;  // zeroed before launch
     uint32_t *status;         // device word, bit0 = internal buffer overflow (a bug if ever set)
     int grid;                 // number of CTAs (= SM count)
+    float score_floor;        // rows scoring below this are never candidates (-inf = none); distance_limit pushed down
 };
 // K2: streaming scan + fused per-CTA top-k' (replaces usearch Index::search,
 // src/search/search_provider.rs:214).
@@ -158,6 +159,8 @@ struct ScanLaunchI8 {
     uint32_t *chunk_counter;
     uint32_t *status;
     int grid;
+    const float *eps_q;       // [nq] bound on |scan score - exact score| per query (prep_queries_i8)
+    float limit_score;        // 1 - distance_limit, -inf = none; the kernel's floor is limit_score - 2 eps_q
 };
 cudaError_t launch_scan_topk_i8(const ScanLaunchI8 &p, cudaStream_t s);
 cudaError_t launch_prep_queries_i8(const float *q32, int n_queries, I8Query *out, float *eps_q, cudaStream_t s);

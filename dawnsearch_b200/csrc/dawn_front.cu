@@ -91,21 +91,7 @@ int dawn_decode_i24(const uint8_t *in1152, float *out384) {
 }
 
 // ------------------------------------------------------------------ (f3) distance limit
-
-// Like dawn_index_search, but hits with distance >= distance_limit are dropped (results are
-// ascending, so this truncates).  limit = +inf (or NaN) keeps everything.
-int dawn_index_search_limit(dawn_index *idx, const float *query384, size_t k, float distance_limit,
-                            uint64_t *labels_out, float *distances_out, size_t *count_out) {
-    int rc = dawn_index_search(idx, query384, k, labels_out, distances_out, count_out);
-    if (rc != DAWN_OK) return rc;
-    size_t n = *count_out;
-    if (distance_limit == distance_limit) {
-        size_t keep = 0;
-        while (keep < n && distances_out[keep] < distance_limit) keep++;
-        *count_out = keep;
-    }
-    return DAWN_OK;
-}
+// dawn_index_search_limit lives in dawn_index.cu: the limit is pushed down into the scan kernels.
 
 // The peer side of UdpPacket::Search: raw 1152-byte i24 query in, hits below the limit out
 // (udp_service.rs:174-213 without the SQLite hydration).  has_limit = 0 mirrors `None`.

@@ -84,6 +84,7 @@ struct dawn_index {
     // search costs a single D2H copy
     uint8_t *d_result = nullptr, *h_result = nullptr;
     size_t result_cap = 0;
+    float limit_score = -INFINITY;  // 1 - distance_limit of the search being enqueued (scan paths push it down)
     bool counters_clean = false;  // finalize leaves the chunk counters / status word zeroed for the next search
     Cand *d_partials = nullptr;
     size_t partials_cap = 0;
@@ -379,6 +380,8 @@ int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, s
             sl.chunk_counter = idx->d_counters + 1 + pass;
             sl.status = idx->d_counters;
             sl.grid = grid;
+            sl.eps_q = d_eps + done;
+            sl.limit_score = idx->limit_score;
             EventPair ev;
             bool timed = begin_event(idx, 0, s, &ev);
             CK(idx, launch_scan_topk_i8(sl, s));
@@ -526,6 +529,7 @@ int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, s
         sl.chunk_counter = idx->d_counters + 1 + pass;
         sl.status = idx->d_counters;
         sl.grid = grid;
+        sl.score_floor = idx->limit_score > -INFINITY ? idx->limit_score - 2.0f * kScanEps - 1e-6f : -INFINITY;
         EventPair ev;
         bool timed = begin_event(idx, 0, s, &ev);
         CK(idx, launch_scan_topk_f16(sl, s));
@@ -737,8 +741,43 @@ int dawn_index_add_synthetic(dawn_index *idx, uint64_t seed, uint64_t first_row,
     return DAWN_OK;
 }
 
+namespace {
+struct LimitScope {  // the pushed-down limit applies to one host call only
+    dawn_index *idx;
+    LimitScope(dawn_index *i, float distance_limit) : idx(i) {
+        if (distance_limit == distance_limit && distance_limit < INFINITY)
+            idx->limit_score = (float)(1.0 - (double)distance_limit);
+    }
+    ~LimitScope() { idx->limit_score = -INFINITY; }
+};
+int search_batch_host(dawn_index *idx, const float *queries, size_t batch, size_t k, float distance_limit,
+                      uint64_t *labels_out, float *distances_out, size_t *counts_out);
+}  // namespace
+
 int dawn_index_search_batch(dawn_index *idx, const float *queries, size_t batch, size_t k,
                             uint64_t *labels_out, float *distances_out, size_t *counts_out) {
+    return search_batch_host(idx, queries, batch, k, NAN, labels_out, distances_out, counts_out);
+}
+
+// (f3) distance_limit of UdpPacket::Search (/root/reference/src/net/udp_packets.rs:29-39): hits with
+// distance >= limit are not returned (src/net/udp_service.rs:196-199).  Results are ascending, so the
+// filter truncates; the limit is also pushed down into the scan kernels as a score floor, so rows that
+// cannot pass it are never appended, merged or re-scored.  limit = +inf or NaN keeps everything.
+int dawn_index_search_limit(dawn_index *idx, const float *query384, size_t k, float distance_limit,
+                            uint64_t *labels_out, float *distances_out, size_t *count_out) {
+    int rc = search_batch_host(idx, query384, 1, k, distance_limit, labels_out, distances_out, count_out);
+    if (rc != DAWN_OK) return rc;
+    if (distance_limit == distance_limit) {
+        size_t keep = 0;
+        while (keep < *count_out && distances_out[keep] < distance_limit) keep++;
+        *count_out = keep;
+    }
+    return DAWN_OK;
+}
+
+namespace {
+int search_batch_host(dawn_index *idx, const float *queries, size_t batch, size_t k, float distance_limit,
+                      uint64_t *labels_out, float *distances_out, size_t *counts_out) {
     int rc = check_alive(idx);
     if (rc) return rc;
     if (batch == 0) return DAWN_OK;
@@ -746,6 +785,7 @@ int dawn_index_search_batch(dawn_index *idx, const float *queries, size_t batch,
     if (k > DAWN_MAX_K) return fail(DAWN_ERR_INVALID, "k = %zu exceeds DAWN_MAX_K = %d", k, DAWN_MAX_K);
     if (k > 0 && (!labels_out || !distances_out)) return fail(DAWN_ERR_INVALID, "output buffer is null");
     std::lock_guard<std::mutex> lk(idx->mu);
+    LimitScope limit_scope(idx, distance_limit);
     rc = flush_staged(idx);
     if (rc) return rc;
     if (k == 0 || idx->size == 0) {
@@ -794,6 +834,7 @@ int dawn_index_search_batch(dawn_index *idx, const float *queries, size_t batch,
     }
     return DAWN_OK;
 }
+}  // namespace
 
 int dawn_index_search(dawn_index *idx, const float *query384, size_t k, uint64_t *labels_out,
                       float *distances_out, size_t *count_out) {

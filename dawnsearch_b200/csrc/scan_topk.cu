@@ -118,6 +118,7 @@ struct ScanSmem {
     uint32_t cnt[QT];
     uint32_t list_len[QT];
     float thr[QT];
+    float floor[QT];  // scores below this are never candidates (distance_limit pushed down; -inf = none)
     uint32_t done_warps;
     uint32_t overflow;
 };
@@ -183,7 +184,7 @@ __device__ __forceinline__ void prune(Smem &sm, int kprime, int tid) {
             int new_len = min(total, kprime);
             sm.list_len[q] = new_len;
             sm.cnt[q] = 0;
-            sm.thr[q] = new_len == kprime ? sm.list[q][kprime - 1].score : __int_as_float(0xff800000);
+            sm.thr[q] = new_len == kprime ? sm.list[q][kprime - 1].score : sm.floor[q];
         }
     }
     consumer_bar_sync();
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restrict__ labels,
                      uint32_t n_rows, const float *__restrict__ queries, int kprime,
                      Cand *__restrict__ partials, uint32_t *__restrict__ chunk_counter,
-                     uint32_t *__restrict__ status) {
+                     uint32_t *__restrict__ status, float score_floor) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     ScanSmem<QT> &sm = *reinterpret_cast<ScanSmem<QT> *>(smem_raw);
     const int tid = threadIdx.x;
@@ -214,7 +215,8 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
     if (tid < QT) {
         sm.cnt[tid] = 0;
         sm.list_len[tid] = 0;
-        sm.thr[tid] = __int_as_float(0xff800000);
+        sm.thr[tid] = score_floor;
+        sm.floor[tid] = score_floor;
     }
     __syncthreads();
     if (tid == 0) SCAN_TRACE(1);
@@ -278,7 +280,7 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
 #pragma unroll
     for (int q = 0; q < QT; q++) qmask[q] = __ballot_sync(0xffffffffu, my_q == q && is_rep);
 
-    float thr = __int_as_float(0xff800000);
+    float thr = score_floor;
     uint32_t g = warp;
     if (tid == 0) SCAN_TRACE(4);
     while (true) {
@@ -441,7 +443,8 @@ template <int QT>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restrict__ labels, uint32_t n_rows,
                     const I8Query *__restrict__ queries, int kprime, Cand *__restrict__ partials,
-                    uint32_t *__restrict__ chunk_counter, uint32_t *__restrict__ status) {
+                    uint32_t *__restrict__ chunk_counter, uint32_t *__restrict__ status,
+                    const float *__restrict__ eps_q, float limit_score) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     ScanSmemI8<QT> &sm = *reinterpret_cast<ScanSmemI8<QT> *>(smem_raw);
     const int tid = threadIdx.x;
@@ -460,7 +463,12 @@ scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restri
     if (tid < QT) {
         sm.cnt[tid] = 0;
         sm.list_len[tid] = 0;
-        sm.thr[tid] = __int_as_float(0xff800000);
+        // distance_limit pushed down: a row whose scan score is below limit_score - 2 eps_q has an exact
+        // distance above the limit
+        const float f = limit_score > __int_as_float(0xff800000) ? limit_score - 2.0f * eps_q[tid] - 1e-6f
+                                                                  : __int_as_float(0xff800000);
+        sm.thr[tid] = f;
+        sm.floor[tid] = f;
     }
     __syncthreads();
 
@@ -533,7 +541,7 @@ scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restri
 #pragma unroll
     for (int q = 0; q < QT; q++) qmask[q] = __ballot_sync(0xffffffffu, my_q == q && is_rep);
 
-    float thr = __int_as_float(0xff800000);
+    float thr = ((volatile float *)sm.thr)[my_q];
     uint32_t g = warp;
     while (true) {
         {   // join a prune if any query's buffer reached the high-water mark (no slot is held here)
@@ -710,7 +718,8 @@ cudaError_t launch_i8_qt(const ScanLaunchI8 &p, cudaStream_t s) {
         configured[dev] = true;
     }
     scan_topk_i8_kernel<QT><<<p.grid, kScanThreads, smem, s>>>(p.corpus, p.labels, p.n_rows, p.queries, p.kprime,
-                                                              p.partials, p.chunk_counter, p.status);
+                                                              p.partials, p.chunk_counter, p.status, p.eps_q,
+                                                              p.limit_score);
     return cudaGetLastError();
 }
 
@@ -727,7 +736,7 @@ cudaError_t launch_qt(const ScanLaunch &p, cudaStream_t s) {
         configured[dev] = true;
     }
     scan_topk_f16_kernel<QT><<<p.grid, kScanThreads, smem, s>>>(
-        p.corpus, p.labels, p.n_rows, p.queries, p.kprime, p.partials, p.chunk_counter, p.status);
+        p.corpus, p.labels, p.n_rows, p.queries, p.kprime, p.partials, p.chunk_counter, p.status, p.score_floor);
     return cudaGetLastError();
 }
 

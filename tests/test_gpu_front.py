@@ -61,6 +61,42 @@ def test_distance_limit_drops_far_hits(small, oracle):
     assert len(idx.search_limit(q, 20, -1.0).labels) == 0
 
 
+@pytest.mark.parametrize("scalar", ["f16", "i8"])
+def test_distance_limit_pushed_into_the_scan_is_exact(dawn, oracle, scalar):
+    """The limit is a score floor inside the scan kernels: whatever its value, the hits must be exactly the
+    oracle's hits with distance < limit (bit-identical, same order), for fp16 and int8 storage."""
+    n = 30_000
+    rows = oracle.np_synth_rows_f32(SEED + 3, 0, n)
+    labels = np.arange(1, n + 1, dtype=np.uint64)
+    if scalar == "i8":
+        opts = dawn.IndexOptions(quantization=dawn.ScalarKind.I8)
+        stored = oracle.store_i8(rows)
+        ref = lambda q, k: oracle.search_i8(stored[0], stored[1], labels, q, k)
+    else:
+        opts = dawn.IndexOptions()
+        stored = oracle.store_f16(rows)
+        ref = lambda q, k: oracle.search_f16(stored, labels, q, k)
+    with dawn.new_index(opts) as idx:
+        idx.reserve(n)
+        idx.add_batch(labels, rows)
+        for q in oracle.make_queries(SEED + 3, 9, 4, n):
+            for k in (20, 100):
+                wl, wd = ref(q, k)
+                limits = [float(wd[0]), float(wd[1]), float(wd[k // 2]), float(wd[-1]),
+                          float(np.nextafter(wd[3], np.float32(2))), float(wd[-1]) + 0.5, 0.0]
+                for lim in limits:
+                    keep = int((wd < np.float32(lim)).sum())
+                    m = idx.search_limit(q, k, lim)
+                    assert len(m.labels) == keep, (scalar, k, lim)
+                    assert (m.labels == wl[:keep]).all() and (bits(m.distances) == bits(wd[:keep])).all()
+        # the next unlimited search is not affected by the previous limit
+        q = oracle.make_queries(SEED + 3, 10, 1, n)[0]
+        idx.search_limit(q, 20, 0.1)
+        wl, wd = ref(q, 20)
+        m = idx.search(q, 20)
+        assert (m.labels == wl).all() and (bits(m.distances) == bits(wd)).all()
+
+
 def test_i24_wire_query_and_stored_vector(dawn, small, oracle):
     idx, rows, stored = small
     q = oracle.make_queries(SEED, 6, 1, len(rows))[0]

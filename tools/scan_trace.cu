@@ -34,7 +34,7 @@ int main(int argc, char **argv) {
     }
     ScanLaunch p{};
     p.corpus = corpus; p.labels = nullptr; p.n_rows = n; p.queries = q; p.nq = 1; p.kprime = kp;
-    p.partials = partials; p.chunk_counter = ctr; p.status = ctr + 1; p.grid = 148;
+    p.partials = partials; p.chunk_counter = ctr; p.status = ctr + 1; p.grid = 148; p.score_floor = -INFINITY;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9f;
