@@ -18,6 +18,20 @@
 
 namespace dawn {
 
+#ifdef DAWN_SCAN_TRACE  // tools/scan_trace.cu only
+__device__ unsigned long long g_fin_trace[16];
+#define FIN_TRACE(slot)                                                       \
+    do {                                                                      \
+        if (threadIdx.x == 0 && blockIdx.x == 0) {                            \
+            unsigned long long t_;                                            \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));            \
+            g_fin_trace[slot] = t_;                                           \
+        }                                                                     \
+    } while (0)
+#else
+#define FIN_TRACE(slot) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kFinThreads = 1024;     // merging 148 per-CTA lists (scan path)
@@ -27,7 +41,7 @@ constexpr int kFinItems = kFinCapEntries / kFinThreads;
 
 struct FinSmem {
     alignas(16) float q[kDim];
-    float scan_score[kMaxCand];
+    uint32_t warp_min[kMaxCand / 32];
     uint32_t n_valid;
     float kth_dist;
     uint32_t n_surv;
@@ -97,28 +111,65 @@ __device__ void merge_lists(Cand *S, int n_lists, int kp, int tid) {
 // and the caller falls back to the tree merge.
 constexpr int kSelProbeMax = 512;
 constexpr int kSelSurvCap = 1024;
+
+// How many of arr[0..n) come before `me`: by Cand::score (descending if DESC, else ascending), equal scores by
+// (label asc, row asc).  The loop compares scores only and is shared by 1 << shift adjacent lanes; the
+// label / row tie-break is a second pass run only when an equal score was actually met.  `self_in` = 1 if
+// `me` is itself an element of arr.  Every lane of the warp must call (shuffles); the result is valid on sub == 0.
+template <bool DESC>
+__device__ __forceinline__ int count_before(const Cand *arr, int n, const Cand &me, bool active, int sub, int shift,
+                                            int self_in) {
+    int before = 0, eq = 0;
+    const float ms = me.score;
+    if (active) {
+#pragma unroll 8
+        for (int j = sub; j < n; j += 1 << shift) {
+            const float s = arr[j].score;
+            before += (DESC ? s > ms : s < ms) ? 1 : 0;
+            eq += s == ms ? 1 : 0;
+        }
+    }
+    for (int o = 1; o < (1 << shift); o <<= 1) {
+        before += __shfl_xor_sync(0xffffffffu, before, o);
+        eq += __shfl_xor_sync(0xffffffffu, eq, o);
+    }
+    if (active && sub == 0 && eq > self_in) {
+        for (int j = 0; j < n; j++) {
+            const Cand o = arr[j];
+            if (o.score == ms && (o.label < me.label || (o.label == me.label && o.row < me.row))) before++;
+        }
+    }
+    return before;
+}
+
 __device__ bool select_lists(const Cand *__restrict__ lists, int n_lists, int kp, FinSmem &sm, int tid) {
     Cand *S = sm.s;
     Cand *surv = S + kSelSurvCap;                                   // [kSelSurvCap]
     float *probe = reinterpret_cast<float *>(S + 2 * kSelSurvCap);  // [kSelProbeMax]
     const int m = (kp + n_lists - 1) / n_lists;
     const int n_probe = n_lists * m;
-    float mine = 0.0f;
-    if (tid < n_probe) {
-        mine = lists[(size_t)(tid / m) * kp + (tid % m)].score;
-        probe[tid] = mine;
-    }
+    if (tid < n_probe) probe[tid] = lists[(size_t)(tid / m) * kp + (tid % m)].score;
     if (tid == 0) sm.n_surv = 0u;
     __syncthreads();
-    if (tid < n_probe) {
+    FIN_TRACE(1);
+    {   // kp-th best probe (ties by index so that exactly one probe has that rank)
+        const int shift = n_probe <= kFinThreads / 4 ? 2 : 1;
+        const int ent = tid >> shift, sub = tid & ((1 << shift) - 1);
+        const bool active = ent < n_probe;
+        const float mine = active ? probe[ent] : 0.0f;
         int rank = 0;
-        for (int j = 0; j < n_probe; j++) {
-            const float o = probe[j];
-            rank += (o > mine || (o == mine && j < tid)) ? 1 : 0;
+        if (active) {
+#pragma unroll 8
+            for (int j = sub; j < n_probe; j += 1 << shift) {
+                const float o = probe[j];
+                rank += (o > mine || (o == mine && j < ent)) ? 1 : 0;
+            }
         }
-        if (rank == kp - 1) sm.bound = mine;
+        for (int o = 1; o < (1 << shift); o <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+        if (active && sub == 0 && rank == kp - 1) sm.bound = mine;
     }
     __syncthreads();
+    FIN_TRACE(2);
     const float lb = sm.bound;
     const int total = n_lists * kp;
 #pragma unroll 4
@@ -130,15 +181,18 @@ __device__ bool select_lists(const Cand *__restrict__ lists, int n_lists, int kp
         }
     }
     __syncthreads();
+    FIN_TRACE(3);
     const int n_surv = (int)sm.n_surv;
     if (n_surv > kSelSurvCap) return false;
-    if (tid < n_surv) {
-        const Cand me = surv[tid];
-        int rank = 0;
-        for (int j = 0; j < n_surv; j++) rank += cand_better(surv[j], me) ? 1 : 0;
-        if (rank < kp) S[rank] = me;
-    } else if (tid < kp) {
-        S[tid] = empty_cand();  // fewer than kp valid candidates in all lists together
+    {
+        const int shift = n_surv <= kFinThreads / 4 ? 2 : n_surv <= kFinThreads / 2 ? 1 : 0;
+        const int ent = tid >> shift, sub = tid & ((1 << shift) - 1);
+        const bool active = ent < n_surv;
+        Cand me = empty_cand();
+        if (active) me = surv[ent];
+        const int rank = count_before<true>(surv, n_surv, me, active, sub, shift, 1);
+        if (active && sub == 0 && rank < kp) S[rank] = me;
+        if (tid >= n_surv && tid < kp) S[tid] = empty_cand();  // fewer than kp valid candidates in all lists together
     }
     return true;
 }
@@ -157,6 +211,7 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
     const Cand *lists = partials + (size_t)qi * n_lists * kp;
 
     const int nthr = blockDim.x;
+    FIN_TRACE(0);
     for (int c = tid; c < kDim; c += nthr) sm.q[c] = queries[(size_t)qi * kDim + c];
 
     // ---- K5: streaming tree merge, cap_lists lists per round, list 0 is the running result
@@ -181,6 +236,7 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
         }
     }
     __syncthreads();
+    FIN_TRACE(4);
 
     // ---- K6: exact re-score.  The survivors' rows are first staged in shared memory by the whole CTA
     // (coalesced, one round trip to L2/HBM), then one thread per candidate adds the 384 products
@@ -200,10 +256,12 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
         }
     }
     __syncthreads();
+    FIN_TRACE(5);
     Cand mine = empty_cand();
+    float my_scan = __int_as_float(0x7f800000);  // scan score of this candidate (+inf for an empty slot)
     if (tid < kp) {
         mine = sm.s[tid];
-        sm.scan_score[tid] = mine.row != kNoRow ? mine.score : __int_as_float(0x7f800000);
+        my_scan = mine.row != kNoRow ? mine.score : __int_as_float(0x7f800000);
         if (mine.row != kNoRow) {
             float acc = 0.0f;
             const uint4 *rp = stage_rows
@@ -237,32 +295,30 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
             mine.score = __fsub_rn(1.0f, acc);  // distance, vector.rs:133
         }
     }
-    __syncthreads();
+    __syncthreads();  // every read of the merged list is done before it is overwritten with distances
+    FIN_TRACE(6);
     // From here on Cand::score holds the DISTANCE (smaller is better); empty slots get +inf.
+    const bool valid = tid < kp && mine.row != kNoRow;
     if (tid < kp) {
         if (mine.row == kNoRow) mine.score = __int_as_float(0x7f800000);
         sm.s[tid] = mine;
     }
-    __syncthreads();
+    if (tid < kMaxCand) {  // weakest scan score among the candidates, one value per warp
+        const uint32_t w = __reduce_min_sync(0xffffffffu, float_to_ordered(my_scan));
+        if ((tid & 31) == 0) sm.warp_min[tid >> 5] = w;
+    }
+    const int n_valid = __syncthreads_count(valid ? 1 : 0);
 
     // ---- final order: distance asc, label asc, row asc (rank counting over <= 128 entries).
     // Ordering on the emitted f32 distance (not the score) makes the output self-consistent
     // and lets sharded results be merged from (label, distance) pairs alone.
-    int rank = 0;
-    const bool valid = tid < kp && mine.row != kNoRow;
-    if (valid) {
-        for (int j = 0; j < kp; j++) rank += dist_before(sm.s[j], mine) ? 1 : 0;
-    }
-    const unsigned n_valid_warp = __popc(__ballot_sync(0xffffffffu, valid));
-    if (tid == 0) sm.n_valid = 0;
-    __syncthreads();
-    if ((tid & 31) == 0 && n_valid_warp) atomicAdd(&sm.n_valid, n_valid_warp);
-    __syncthreads();
-    const int n_valid = (int)sm.n_valid;
-    if (valid && rank < k) {
-        labels_out[(size_t)qi * k + rank] = mine.label;
-        distances_out[(size_t)qi * k + rank] = mine.score;
-        if (rank == k - 1) sm.kth_dist = mine.score;
+    if (tid < kMaxCand) {
+        const int rank = count_before<false>(sm.s, kp, mine, valid, 0, 0, 1);
+        if (valid && rank < k) {
+            labels_out[(size_t)qi * k + rank] = mine.label;
+            distances_out[(size_t)qi * k + rank] = mine.score;
+            if (rank == k - 1) sm.kth_dist = mine.score;
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -273,20 +329,23 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
             // <= scan_min + eps and distance >= 1 - (scan_min + eps); it cannot displace or tie
             // the k-th result if that bound is strictly above the k-th distance.
             const float e = eps_q ? eps_q[qi] : eps;
-            float scan_min = sm.scan_score[0];  // weakest kept candidate (lists need not be sorted)
-            for (int j = 1; j < kp; j++) scan_min = fminf(scan_min, sm.scan_score[j]);
+            uint32_t wmin = sm.warp_min[0];
+            for (int w = 1; w < (kp + 31) / 32; w++) wmin = min(wmin, sm.warp_min[w]);
+            const float scan_min = ordered_to_float(wmin);  // weakest kept candidate (lists need not be sorted)
             const float bound = __fsub_rn(1.0f, __fadd_rn(scan_min, e));
             certified = bound > sm.kth_dist;
         }
         if (overflow && overflow[qi]) certified = false;  // candidates were lost: cannot certify
         flags_out[qi] = certified ? 1u : 0u;
     }
+    FIN_TRACE(7);
     // the last kernel of a search leaves the chunk counters / status word clean for the next one
     if (blockIdx.x == 0 && counters) {
         if (tid == 0 && status_out) *status_out = counters[0];
         __syncthreads();
         for (int i = tid; i < n_counters; i += nthr) counters[i] = 0u;
     }
+    FIN_TRACE(8);
 }
 
 }  // namespace

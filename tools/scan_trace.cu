@@ -3,6 +3,7 @@
 //        tools/scan_trace.cu -o tools/bin/scan_trace
 // Includes the kernel source directly so the library build stays free of trace code.
 #include "../dawnsearch_b200/csrc/scan_topk.cu"
+#include "../dawnsearch_b200/csrc/finalize.cu"
 
 #include <algorithm>
 #include <cstdio>
@@ -69,5 +70,30 @@ int main(int argc, char **argv) {
     for (int c = 0; c < 148; c++) { pr += tr[c][9] * 1e-3; np += tr[c][10]; nf += tr[c][11]; }
     printf("  in-scan prunes per CTA %.2f, %.2f us each; end-of-stream prune rounds per CTA %.2f\n", np / 148,
            np ? pr / np : 0.0, nf / 148);
+
+    // ---- finalize (K5 + K6) over the lists the scan just wrote
+    uint64_t *d_labels; float *d_dist; uint32_t *d_cnt;
+    cudaMalloc(&d_labels, 128 * 8); cudaMalloc(&d_dist, 128 * 4); cudaMalloc(&d_cnt, 64);
+    FinalizeLaunch f{};
+    f.corpus = corpus; f.queries = q; f.nq = 1; f.partials = partials; f.n_lists = 148; f.kprime = kp;
+    f.k = kp >= 32 ? 20 : 10; f.eps = 3e-5f; f.labels_out = d_labels; f.distances_out = d_dist; f.counts_out = d_cnt;
+    f.flags_out = d_cnt + 1; f.scalar = 0; f.eps_q = nullptr; f.overflow = nullptr; f.counters = ctr; f.n_counters = 2;
+    f.status_out = d_cnt + 2;
+    best = 1e9f;
+    for (int it = 0; it < 30; it++) {
+        cudaDeviceSynchronize();
+        cudaEventRecord(e0);
+        launch_finalize(f, 0);
+        cudaEventRecord(e1);
+        cudaDeviceSynchronize();
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        best = std::min(best, ms);
+    }
+    unsigned long long ft[16];
+    cudaMemcpyFromSymbol(ft, g_fin_trace, sizeof(ft));
+    printf("finalize: best %.2f us by events; in-kernel timeline (us from entry):\n", best * 1e3f);
+    const char *fn[9] = {"entry", "probe loaded", "bound found", "filtered", "merged list ready", "rows staged",
+                         "re-scored", "results written", "exit"};
+    for (int s = 0; s < 9; s++) printf("  %-20s %7.2f\n", fn[s], (ft[s] - ft[0]) * 1e-3);
     return 0;
 }
