@@ -181,6 +181,7 @@ struct GemmSearch {
     int cta_group;            // 0 = auto (pairs when more than 128 queries), 1 or 2 to force
     int chunk_tiles;          // 0 = auto; tiles per work unit (tuning override)
     int sequential_tiles;     // 1 = visit tiles in stored order instead of the strided permutation (A/B only)
+    int growth;               // rows visited grow by this factor per round (0 = automatic: 8, or up to 32 for one query tile)
     void *workspace;          // gemm_workspace_bytes(n_queries)
     Cand *final_lists;        // out: [ceil128(n_queries)][kprime] sorted candidates (approximate scores)
     float accum_slack;        // bound on the tensor-core accumulation error added to every eps_q

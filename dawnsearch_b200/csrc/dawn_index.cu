@@ -102,6 +102,7 @@ struct dawn_index {
     int64_t gemm_cta_group = 0;  // 0 auto, 1 = one CTA per tile, 2 = CTA pairs
     int64_t gemm_chunk_tiles = 0;  // 0 auto
     int64_t gemm_sequential_tiles = 0;
+    int64_t gemm_growth = 0;  // 0 = automatic
 
     // The search workspace (partials, counters, K3 logs) is shared by all searches on this handle:
     // a search enqueued on another stream than the previous one first waits for it.
@@ -455,6 +456,7 @@ int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, s
         gs.cta_group = (int)idx->gemm_cta_group;
         gs.chunk_tiles = (int)idx->gemm_chunk_tiles;
         gs.sequential_tiles = (int)idx->gemm_sequential_tiles;
+        gs.growth = (int)idx->gemm_growth;
         gs.workspace = idx->d_gemm_ws;
         gs.final_lists = idx->d_partials;
         gs.accum_slack = kGemmAccumSlack;
@@ -1012,6 +1014,7 @@ int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value) {
     else if (!strcmp(key, "gemm_cta_group")) idx->gemm_cta_group = value;
     else if (!strcmp(key, "gemm_chunk_tiles")) idx->gemm_chunk_tiles = value;
     else if (!strcmp(key, "gemm_sequential_tiles")) idx->gemm_sequential_tiles = value;
+    else if (!strcmp(key, "gemm_growth")) idx->gemm_growth = value;
     else return fail(DAWN_ERR_INVALID, "unknown option '%s'", key);
     return DAWN_OK;
 }

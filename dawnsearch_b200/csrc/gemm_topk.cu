@@ -713,10 +713,16 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
     // round, which must fit the 2048-entry log with margin); every boundary is a multiple of the
     // tile height.  Compute-bound batches use x8 (fewest survivors to handle); HBM-bound batches
     // (one query tile: the epilogue has slack) use up to x32 to save rounds.
-    uint64_t growth = 8;
+    // With k' = 128 a x8 round leaves ~900 survivors per query and the epilogue's slow path becomes the
+    // bottleneck of the early rounds; x4 measured ~5 % faster at batch 1024, k = 100 (tools/ab_gemm.py).
+    uint64_t growth = p.kprime > 64 ? 4 : 8;
     if (n_qtiles == 1 && cg == 1) {
         growth = 32;
         while (growth > 8 && (growth - 1) * (uint64_t)p.kprime * 5 / 4 + (uint64_t)p.kprime > (uint64_t)kSelCap) growth /= 2;
+    }
+    if (p.growth >= 2) {  // tuning override, clamped so that a round's survivors fit the log
+        growth = (uint64_t)p.growth;
+        while (growth > 2 && (growth - 1) * (uint64_t)p.kprime * 5 / 4 + (uint64_t)p.kprime > (uint64_t)kSelCap) growth /= 2;
     }
     const uint64_t total_tiles = (p.n_rows + BN - 1) / BN;
     // stride of the visiting permutation: about 0.618 * total, made coprime to total

@@ -8,7 +8,9 @@ from dawnsearch_b200 import synth
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 50_000_000
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 10
-settings = [dict(gemm_sequential_tiles=v) for v in (0, 1)]
+knob = sys.argv[4] if len(sys.argv) > 4 else "gemm_sequential_tiles"
+values = [int(v) for v in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0, 1]
+settings = [{knob: v} for v in values]
 idx = D.new_index(D.IndexOptions(capacity=rows))
 idx.add_synthetic(0xDA5EA2C4, 0, rows)
 dev = torch.device("cuda:0")
