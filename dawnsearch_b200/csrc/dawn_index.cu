@@ -269,6 +269,8 @@ struct ResultView {
     uint32_t *counts, *flags, *status;
     size_t bytes;
 };
+constexpr size_t kDirectResultBytes = 4096;  // result blocks up to this size are written to host memory by the kernel
+
 inline ResultView result_view(uint8_t *base, size_t batch, size_t k) {
     ResultView v;
     v.labels = reinterpret_cast<uint64_t *>(base);
@@ -802,9 +804,16 @@ int search_batch_host(dawn_index *idx, const float *queries, size_t batch, size_
     int kprime = choose_kprime(k);
     const uint64_t gemm_before = idx->prof.gemm_batches;
     ResultView dv = result_view(idx->d_result, batch, k), hv = result_view(idx->h_result, batch, k);
-    rc = search_enqueue(idx, idx->d_queries, batch, k, kprime, dv.labels, dv.dist, dv.counts, dv.flags, s, false, dv.status);
+    // A small result block is written by the finalize kernel straight into the pinned host buffer (it is
+    // device-accessible under unified addressing): a few hundred bytes of posted PCIe writes instead of a
+    // copy-engine round trip after the kernel.  Large blocks go through one D2H copy.
+    // (Passing the single query by value as a launch parameter instead of the H2D copy was tried as well:
+    // no gain, the copy already overlaps the launches.)
+    const bool direct = dv.bytes <= kDirectResultBytes;
+    const ResultView &ov = direct ? hv : dv;
+    rc = search_enqueue(idx, idx->d_queries, batch, k, kprime, ov.labels, ov.dist, ov.counts, ov.flags, s, false, ov.status);
     if (rc) return rc;
-    CK(idx, cudaMemcpyAsync(idx->h_result, idx->d_result, dv.bytes, cudaMemcpyDeviceToHost, s));  // the one D2H
+    if (!direct) CK(idx, cudaMemcpyAsync(idx->h_result, idx->d_result, dv.bytes, cudaMemcpyDeviceToHost, s));  // the one D2H
     CK(idx, cudaStreamSynchronize(s));
     if (hv.status[0] != 0) return fail(DAWN_ERR_INTERNAL, "scan kernel reported status 0x%x", hv.status[0]);
     memcpy(labels_out, hv.labels, batch * k * sizeof(uint64_t));
@@ -824,10 +833,12 @@ int search_batch_host(dawn_index *idx, const float *queries, size_t batch, size_
     for (size_t b : redo) {
         idx->prof.escalations++;
         ResultView d1 = result_view(idx->d_result, 1, k), h1 = result_view(idx->h_result, 1, k);
-        rc = search_enqueue(idx, idx->d_queries + b * kDim, 1, k, kMaxCand, d1.labels, d1.dist, d1.counts, d1.flags, s,
-                            /*scan_only=*/true, d1.status);
+        const bool direct1 = d1.bytes <= kDirectResultBytes;
+        const ResultView &o1 = direct1 ? h1 : d1;
+        rc = search_enqueue(idx, idx->d_queries + b * kDim, 1, k, kMaxCand, o1.labels, o1.dist, o1.counts, o1.flags, s,
+                            /*scan_only=*/true, o1.status);
         if (rc) return rc;
-        CK(idx, cudaMemcpyAsync(idx->h_result, idx->d_result, d1.bytes, cudaMemcpyDeviceToHost, s));
+        if (!direct1) CK(idx, cudaMemcpyAsync(idx->h_result, idx->d_result, d1.bytes, cudaMemcpyDeviceToHost, s));
         CK(idx, cudaStreamSynchronize(s));
         memcpy(labels_out + b * k, h1.labels, k * sizeof(uint64_t));
         memcpy(distances_out + b * k, h1.dist, k * sizeof(float));
