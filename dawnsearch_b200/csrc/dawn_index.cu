@@ -6,7 +6,9 @@
 // compute path launches the kernels in scan_topk.cu / finalize.cu / ingest.cu.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <string>
@@ -254,6 +256,41 @@ int flush_staged(dawn_index *idx) {
     CK(idx, cudaStreamSynchronize(idx->stream));
     idx->stage_busy[0] = idx->stage_busy[1] = false;
     return DAWN_OK;
+}
+
+// DAWN_DEBUG_STAGES=1: wait for each kernel of a search separately (polling, 5 s) and say on stderr which one
+// did not finish.  Debug aid only; never set in tests or benches.
+bool debug_stages() {
+    static const bool on = getenv("DAWN_DEBUG_STAGES") != nullptr;
+    return on;
+}
+void debug_wait(dawn_index *idx, cudaStream_t s, const char *stage) {
+    if (!debug_stages()) return;
+    const auto t0 = std::chrono::steady_clock::now();
+    while (true) {
+        cudaError_t e = cudaStreamQuery(s);
+        if (e == cudaSuccess) {
+            fprintf(stderr, "[dawn debug] %s done\n", stage);
+            return;
+        }
+        if (e != cudaErrorNotReady) {
+            fprintf(stderr, "[dawn debug] %s: %s\n", stage, cudaGetErrorString(e));
+            return;
+        }
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 5.0) {
+            uint32_t c[4] = {0, 0, 0, 0};
+            cudaStream_t side;
+            cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+            if (idx->d_counters) {
+                cudaMemcpyAsync(c, idx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, side);
+                cudaStreamSynchronize(side);
+            }
+            fprintf(stderr, "[dawn debug] %s STILL RUNNING after 5 s (size %zu, counters %u %u %u %u)\n", stage, idx->size, c[0],
+                    c[1], c[2], c[3]);
+            fflush(stderr);
+            return;
+        }
+    }
 }
 
 int choose_kprime(size_t k) {
@@ -538,6 +575,7 @@ int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, s
         bool timed = begin_event(idx, 0, s, &ev);
         CK(idx, launch_scan_topk_f16(sl, s));
         if (timed) end_event(idx, ev, s);
+        debug_wait(idx, s, "scan_topk_f16");
         idx->prof.scan_launches++;
         idx->prof.kernel_launches++;
         done += qt;
@@ -562,9 +600,13 @@ int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, s
     fl.counters = idx->d_counters;
     fl.n_counters = (int)need_counters;
     fl.status_out = d_status_out;
+    if (debug_stages())
+        fprintf(stderr, "[dawn debug] finalize: nq %d lists %d k' %d k %d out %p\n", fl.nq, fl.n_lists, fl.kprime, fl.k,
+                (void *)fl.labels_out);
     EventPair ev;
     bool timed = begin_event(idx, 1, s, &ev);
     CK(idx, launch_finalize(fl, s));
+    debug_wait(idx, s, "finalize (scan path)");
     if (timed) end_event(idx, ev, s);
     idx->prof.finalize_launches++;
     idx->prof.kernel_launches++;
@@ -809,7 +851,7 @@ int search_batch_host(dawn_index *idx, const float *queries, size_t batch, size_
     // copy-engine round trip after the kernel.  Large blocks go through one D2H copy.
     // (Passing the single query by value as a launch parameter instead of the H2D copy was tried as well:
     // no gain, the copy already overlaps the launches.)
-    const bool direct = dv.bytes <= kDirectResultBytes;
+    const bool direct = dv.bytes <= kDirectResultBytes && !getenv("DAWN_NO_DIRECT_RESULT");
     const ResultView &ov = direct ? hv : dv;
     rc = search_enqueue(idx, idx->d_queries, batch, k, kprime, ov.labels, ov.dist, ov.counts, ov.flags, s, false, ov.status);
     if (rc) return rc;

@@ -62,7 +62,18 @@ static_assert(kHighWater >= kMaxCand, "first prune must be able to fill the list
 struct StageMeta {
     uint32_t row_base;
     uint32_t n_rows;  // 0 = end-of-stream sentinel
+    uint32_t stage;   // which stage the slot holds (or is being filled with); 0xffffffff before first use
+    uint32_t pad;
 };
+constexpr uint32_t kNoStage = 0xFFFFFFFFu;
+
+// A consumer that drew ticket g may be a whole ring ahead of the slot's current contents, where a bare
+// parity wait cannot tell "stage g landed" from "stage g - 2*ring landed".  The producer therefore tags the
+// slot with the stage number before it arms the barrier: once the tag reads g, the slot's previous phase has
+// completed and been released, and the parity wait on the current phase is unambiguous.
+__device__ __forceinline__ void wait_stage_tag(const StageMeta *m, uint32_t g) {
+    while (*((volatile const uint32_t *)&m->stage) != g) __nanosleep(20);
+}
 
 // ---- PTX wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -120,6 +131,7 @@ struct ScanSmem {
     float thr[QT];
     float floor[QT];  // scores below this are never candidates (distance_limit pushed down; -inf = none)
     uint32_t done_warps;
+    uint32_t next_stage;  // ticket counter: consumer warps take stages in arrival order
     uint32_t overflow;
 };
 
@@ -209,6 +221,8 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
             mbar_init(&sm.empty_bar[s], 1);
         }
         sm.done_warps = 0;
+        sm.next_stage = 0;
+        for (int st = 0; st < (int)(sizeof(sm.meta) / sizeof(sm.meta[0])); st++) sm.meta[st].stage = kNoStage;
         sm.overflow = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -241,6 +255,7 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
                 const uint32_t nr = min((uint32_t)kStageRows, n_rows - rb);
                 sm.meta[slot].row_base = rb;
                 sm.meta[slot].n_rows = nr;
+                sm.meta[slot].stage = g;
                 mbar_arrive_expect_tx(&sm.full_bar[slot], nr * kRowBytesF16);
                 bulk_g2s(sm.ring[slot], corpus + (size_t)rb * kDim, nr * kRowBytesF16,
                          &sm.full_bar[slot]);
@@ -252,6 +267,7 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
             mbar_wait(&sm.empty_bar[slot], ((g / kStages) & 1u) ^ 1u);
             sm.meta[slot].row_base = 0;
             sm.meta[slot].n_rows = 0;
+            sm.meta[slot].stage = g;
             mbar_arrive(&sm.full_bar[slot]);
         }
         return;
@@ -281,7 +297,6 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
     for (int q = 0; q < QT; q++) qmask[q] = __ballot_sync(0xffffffffu, my_q == q && is_rep);
 
     float thr = score_floor;
-    uint32_t g = warp;
     if (tid == 0) SCAN_TRACE(4);
     while (true) {
         // Join a prune if any query's buffer reached the high-water mark.
@@ -302,9 +317,17 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
                 continue;
             }
         }
+        // Take the next stage by ticket.  (Stages used to belong to warps statically, w, w+16, ...: a warp
+        // waiting at the prune barrier then left its next two landed stages unconsumed, the in-order producer
+        // blocked on their slots, and a warp waiting for a later stage never reached the barrier: deadlock,
+        // seen once a slow append -- a label load queued behind the bulk copies -- put a warp 32 stages behind.)
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(&sm.next_stage, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
         const uint32_t slot = g % kStages;
+        wait_stage_tag(&sm.meta[slot], g);
         mbar_wait(&sm.full_bar[slot], (g / kStages) & 1u);
-        if (tid == 0 && g == 0) SCAN_TRACE(5);
+        if (g == 0 && lane == 0) SCAN_TRACE(5);
         const uint32_t row_base = sm.meta[slot].row_base;
         const uint32_t n_stage_rows = sm.meta[slot].n_rows;
         if (n_stage_rows == 0) break;
@@ -383,7 +406,6 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
                 }
             }
         }
-        g += kConsumerWarps;
     }
 
     // End of this warp's stream: keep joining prunes until every consumer warp is done.
@@ -457,6 +479,8 @@ scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restri
             mbar_init(&sm.empty_bar[s], 1);
         }
         sm.done_warps = 0;
+        sm.next_stage = 0;
+        for (int st = 0; st < (int)(sizeof(sm.meta) / sizeof(sm.meta[0])); st++) sm.meta[st].stage = kNoStage;
         sm.overflow = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -494,6 +518,7 @@ scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restri
                 const uint32_t bytes = ((nr + kI8BlockRows - 1) / kI8BlockRows) * kI8BlockBytes;
                 sm.meta[slot].row_base = rb;
                 sm.meta[slot].n_rows = nr;
+                sm.meta[slot].stage = g;
                 mbar_arrive_expect_tx(&sm.full_bar[slot], bytes);
                 bulk_g2s(sm.ring[slot], corpus + (size_t)blk * kI8StageBytes, bytes, &sm.full_bar[slot]);
             }
@@ -503,6 +528,7 @@ scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restri
             mbar_wait(&sm.empty_bar[slot], ((g / kI8Stages) & 1u) ^ 1u);
             sm.meta[slot].row_base = 0;
             sm.meta[slot].n_rows = 0;
+            sm.meta[slot].stage = g;
             mbar_arrive(&sm.full_bar[slot]);
         }
         return;
@@ -542,7 +568,6 @@ scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restri
     for (int q = 0; q < QT; q++) qmask[q] = __ballot_sync(0xffffffffu, my_q == q && is_rep);
 
     float thr = ((volatile float *)sm.thr)[my_q];
-    uint32_t g = warp;
     while (true) {
         {   // join a prune if any query's buffer reached the high-water mark (no slot is held here)
             uint32_t c = lane < QT ? ((volatile uint32_t *)sm.cnt)[lane] : 0u;
@@ -553,7 +578,11 @@ scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restri
                 continue;
             }
         }
+        uint32_t g = 0;  // next stage by ticket (see the fp16 kernel)
+        if (lane == 0) g = atomicAdd(&sm.next_stage, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
         const uint32_t slot = g % kI8Stages;
+        wait_stage_tag(&sm.meta[slot], g);
         mbar_wait(&sm.full_bar[slot], (g / kI8Stages) & 1u);
         const uint32_t row_base = sm.meta[slot].row_base;
         const uint32_t n_stage_rows = sm.meta[slot].n_rows;
@@ -631,7 +660,6 @@ scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restri
                 }
             }
         }
-        g += kConsumerWarps;
     }
 
     __syncwarp();

@@ -26,7 +26,8 @@ EM_LEN = 384  # src/search/vector.rs:26
 MAX_K = 120
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdawn_b200.so")
+# DAWN_B200_LIB: load another build of the same library (A/B of kernel changes on one box); never a fallback
+LIB_PATH = os.environ.get("DAWN_B200_LIB") or os.path.join(_HERE, "lib", "libdawn_b200.so")
 
 _vp = C.c_void_p
 

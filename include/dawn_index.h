@@ -148,7 +148,8 @@ void dawn_encode_i24(const float *v384, uint8_t *out1152);
 int dawn_decode_i24(const uint8_t *in1152, float *out384);
 
 /* distance_limit of UdpPacket::Search: hits with distance >= limit are not returned
- * (src/net/udp_service.rs:196-199).  NaN limit = no limit. */
+ * (src/net/udp_service.rs:196-199).  NaN limit = no limit.  The limit is also pushed down into the
+ * scan kernels as a score floor, so rows that cannot pass it are never kept, merged or re-scored. */
 int dawn_index_search_limit(dawn_index *idx, const float *query384, size_t k, float distance_limit,
                             uint64_t *labels_out, float *distances_out, size_t *count_out);
 /* The peer side of a remote search: raw i24 query in (udp_service.rs:174-213). */
