@@ -228,6 +228,7 @@ def test_device_generator_is_bit_identical_to_oracle(dawn, oracle):
             assert_same((m.labels, m.distances), oracle.search_f16(want, labels, q, 10))
 
 
+@pytest.mark.timeout(300)
 def test_two_million_rows_against_threaded_cpu_scan(dawn, oracle):
     n = 2_000_000
     with dawn.new_index(dawn.IndexOptions(capacity=n)) as idx:
@@ -242,6 +243,23 @@ def test_two_million_rows_against_threaded_cpu_scan(dawn, oracle):
             assert (bits(gd) == bits(wd)).all()
         prof = idx.profile()
         assert prof["uncertified"] == 0
+        # The same corpus one query at a time (the streaming-scan path, ring slots reused ~50 times per CTA),
+        # first for fp16-path k' = 16, 32 and 128.  Regression: the scan used to hang here when a consumer
+        # warp waited at the prune barrier with landed stages of its own still in the ring.
+        for k in (10, 20, 100):
+            wl, wd, wc, _ = oracle.cpu_scan_f16(stored, None, qs[:6], k)
+            for i in range(6):
+                m = idx.search(qs[i], k)
+                assert_same((m.labels, m.distances), (wl[i][: wc[i]], wd[i][: wc[i]]), f"single query {i} k={k}")
+        # and right after a bulk add (the ingest path), as a rebuild from SQLite would do it
+    rows = oracle.np_synth_rows_f32(SEED + 9, 0, 200_000)
+    labels = np.arange(1, len(rows) + 1, dtype=np.uint64)
+    stored = oracle.store_f16(rows)
+    with dawn.new_index(dawn.IndexOptions(capacity=len(rows))) as idx:
+        idx.add_batch(labels, rows)
+        for k in (1, 10):
+            m = idx.search(rows[0], k)
+            assert_same((m.labels, m.distances), oracle.search_f16(stored, labels, rows[0], k), f"after add_batch k={k}")
 
 
 def test_full_size_properties_10m(dawn, oracle):
