@@ -59,21 +59,13 @@ constexpr int kHighWater = 128;  // >= kMaxCand so the first prune fills the lis
 static_assert(kHighWater + kConsumerWarps * kStageRows <= kBufCap, "append buffer can overflow");
 static_assert(kHighWater >= kMaxCand, "first prune must be able to fill the list");
 
-struct StageMeta {
+struct alignas(16) StageMeta {  // written by the producer lane with ONE 16-byte store (it is the critical path)
     uint32_t row_base;
     uint32_t n_rows;  // 0 = end-of-stream sentinel
     uint32_t stage;   // which stage the slot holds (or is being filled with); 0xffffffff before first use
     uint32_t pad;
 };
 constexpr uint32_t kNoStage = 0xFFFFFFFFu;
-
-// A consumer that drew ticket g may be a whole ring ahead of the slot's current contents, where a bare
-// parity wait cannot tell "stage g landed" from "stage g - 2*ring landed".  The producer therefore tags the
-// slot with the stage number before it arms the barrier: once the tag reads g, the slot's previous phase has
-// completed and been released, and the parity wait on the current phase is unambiguous.
-__device__ __forceinline__ void wait_stage_tag(const StageMeta *m, uint32_t g) {
-    while (*((volatile const uint32_t *)&m->stage) != g) __nanosleep(20);
-}
 
 // ---- PTX wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -114,6 +106,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 __device__ __forceinline__ void consumer_bar_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+}
+
+// A consumer that drew ticket g may be a whole ring ahead of the slot's current contents, where a bare
+// parity wait cannot tell "stage g landed" from "stage g - 2*ring landed".  The producer therefore tags the
+// slot with the stage number before it arms the barrier: once the tag reads g, the slot's previous phase has
+// completed and been released, and the parity wait on the current phase is unambiguous.
+__device__ __forceinline__ void publish_stage(StageMeta *m, uint32_t row_base, uint32_t n_rows, uint32_t g) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(m)), "r"(row_base), "r"(n_rows), "r"(g), "r"(0u)
+                 : "memory");
+}
+__device__ __forceinline__ void wait_stage_tag(const StageMeta *m, uint32_t g) {
+    while (*((volatile const uint32_t *)&m->stage) != g) __nanosleep(20);
 }
 
 // ---- shared-memory layout -------------------------------------------------------------
@@ -253,9 +257,7 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
                 mbar_wait(&sm.empty_bar[slot], ((g / kStages) & 1u) ^ 1u);
                 const uint32_t rb = (uint32_t)row0 + s * kStageRows;
                 const uint32_t nr = min((uint32_t)kStageRows, n_rows - rb);
-                sm.meta[slot].row_base = rb;
-                sm.meta[slot].n_rows = nr;
-                sm.meta[slot].stage = g;
+                publish_stage(&sm.meta[slot], rb, nr, g);
                 mbar_arrive_expect_tx(&sm.full_bar[slot], nr * kRowBytesF16);
                 bulk_g2s(sm.ring[slot], corpus + (size_t)rb * kDim, nr * kRowBytesF16,
                          &sm.full_bar[slot]);
@@ -265,9 +267,7 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
         for (int w = 0; w < kConsumerWarps; w++, g++) {  // one end-of-stream stage per warp
             const uint32_t slot = g % kStages;
             mbar_wait(&sm.empty_bar[slot], ((g / kStages) & 1u) ^ 1u);
-            sm.meta[slot].row_base = 0;
-            sm.meta[slot].n_rows = 0;
-            sm.meta[slot].stage = g;
+            publish_stage(&sm.meta[slot], 0u, 0u, g);
             mbar_arrive(&sm.full_bar[slot]);
         }
         return;
@@ -516,9 +516,7 @@ scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restri
                 const uint32_t nr = min((uint32_t)kI8StageRows, n_rows - rb);
                 // copy only the 8-row blocks that exist (the arena is allocated in whole blocks)
                 const uint32_t bytes = ((nr + kI8BlockRows - 1) / kI8BlockRows) * kI8BlockBytes;
-                sm.meta[slot].row_base = rb;
-                sm.meta[slot].n_rows = nr;
-                sm.meta[slot].stage = g;
+                publish_stage(&sm.meta[slot], rb, nr, g);
                 mbar_arrive_expect_tx(&sm.full_bar[slot], bytes);
                 bulk_g2s(sm.ring[slot], corpus + (size_t)blk * kI8StageBytes, bytes, &sm.full_bar[slot]);
             }
@@ -526,9 +524,7 @@ scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restri
         for (int w = 0; w < kConsumerWarps; w++, g++) {
             const uint32_t slot = g % kI8Stages;
             mbar_wait(&sm.empty_bar[slot], ((g / kI8Stages) & 1u) ^ 1u);
-            sm.meta[slot].row_base = 0;
-            sm.meta[slot].n_rows = 0;
-            sm.meta[slot].stage = g;
+            publish_stage(&sm.meta[slot], 0u, 0u, g);
             mbar_arrive(&sm.full_bar[slot]);
         }
         return;
