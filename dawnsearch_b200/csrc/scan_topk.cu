@@ -62,10 +62,9 @@ static_assert(kHighWater >= kMaxCand, "first prune must be able to fill the list
 struct alignas(16) StageMeta {  // written by the producer lane with ONE 16-byte store (it is the critical path)
     uint32_t row_base;
     uint32_t n_rows;  // 0 = end-of-stream sentinel
-    uint32_t stage;   // which stage the slot holds (or is being filled with); 0xffffffff before first use
+    uint32_t stage;   // which stage the slot holds (debugging aid)
     uint32_t pad;
 };
-constexpr uint32_t kNoStage = 0xFFFFFFFFu;
 
 // ---- PTX wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -95,6 +94,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
                                          uint64_t *bar) {
@@ -108,16 +120,26 @@ __device__ __forceinline__ void consumer_bar_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
 }
 
-// A consumer that drew ticket g may be a whole ring ahead of the slot's current contents, where a bare
-// parity wait cannot tell "stage g landed" from "stage g - 2*ring landed".  The producer therefore tags the
-// slot with the stage number before it arms the barrier: once the tag reads g, the slot's previous phase has
-// completed and been released, and the parity wait on the current phase is unambiguous.
 __device__ __forceinline__ void publish_stage(StageMeta *m, uint32_t row_base, uint32_t n_rows, uint32_t g) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(m)), "r"(row_base), "r"(n_rows), "r"(g), "r"(0u)
                  : "memory");
 }
-__device__ __forceinline__ void wait_stage_tag(const StageMeta *m, uint32_t g) {
-    while (*((volatile const uint32_t *)&m->stage) != g) __nanosleep(20);
+
+// Wait for this warp's next stage -- unless an append buffer reaches its high-water mark first.
+// Warp w owns stages w, w+16, ...  A warp parked at the prune barrier leaves its next two landed stages
+// unconsumed; the in-order producer blocks on their slots; a warp that then sat here in a plain wait for a LATER
+// stage would never reach the barrier: deadlock (seen as a hang of single-query searches over 2M rows, once a slow
+// append -- its label load queued behind the bulk copies -- had put one warp 32 stages behind the others).  So the
+// wait gives up when a prune is due; the stage is simply waited for again afterwards.
+// Returns true if the stage has landed, false if the warp has to join a prune first.
+template <int QT>
+__device__ __forceinline__ bool wait_stage_or_prune(uint64_t *full_bar, uint32_t parity, const uint32_t *cnt, int lane) {
+    while (true) {
+        const bool ok = mbar_try_wait(full_bar, parity);
+        if (__all_sync(0xffffffffu, ok)) return true;
+        const uint32_t c = lane < QT ? ((volatile const uint32_t *)cnt)[lane] : 0u;
+        if (__any_sync(0xffffffffu, c >= (uint32_t)kHighWater)) return false;
+    }
 }
 
 // ---- shared-memory layout -------------------------------------------------------------
@@ -135,7 +157,6 @@ struct ScanSmem {
     float thr[QT];
     float floor[QT];  // scores below this are never candidates (distance_limit pushed down; -inf = none)
     uint32_t done_warps;
-    uint32_t next_stage;  // ticket counter: consumer warps take stages in arrival order
     uint32_t overflow;
 };
 
@@ -225,8 +246,6 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
             mbar_init(&sm.empty_bar[s], 1);
         }
         sm.done_warps = 0;
-        sm.next_stage = 0;
-        for (int st = 0; st < (int)(sizeof(sm.meta) / sizeof(sm.meta[0])); st++) sm.meta[st].stage = kNoStage;
         sm.overflow = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -297,36 +316,31 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
     for (int q = 0; q < QT; q++) qmask[q] = __ballot_sync(0xffffffffu, my_q == q && is_rep);
 
     float thr = score_floor;
+    uint32_t g = warp;
     if (tid == 0) SCAN_TRACE(4);
     while (true) {
-        // Join a prune if any query's buffer reached the high-water mark.
+        // Join a prune if any query's buffer reached the high-water mark -- seen here or while waiting for data.
+        const uint32_t slot = g % kStages;
+        bool landed;
         {
             uint32_t c = lane < QT ? ((volatile uint32_t *)sm.cnt)[lane] : 0u;
-            if (__any_sync(0xffffffffu, c >= (uint32_t)kHighWater)) {
-#ifdef DAWN_SCAN_TRACE
-                unsigned long long tp0, tp1;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp0));
-#endif
-                consumer_bar_sync();
-                prune<QT>(sm, kprime, tid);
-                thr = ((volatile float *)sm.thr)[my_q];
-#ifdef DAWN_SCAN_TRACE
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp1));
-                if (tid == 0) { SCAN_TRACE_ADD(9, tp1 - tp0); SCAN_TRACE_ADD(10, 1ull); }
-#endif
-                continue;
-            }
+            landed = !__any_sync(0xffffffffu, c >= (uint32_t)kHighWater) &&
+                     wait_stage_or_prune<QT>(&sm.full_bar[slot], (g / kStages) & 1u, sm.cnt, lane);
         }
-        // Take the next stage by ticket.  (Stages used to belong to warps statically, w, w+16, ...: a warp
-        // waiting at the prune barrier then left its next two landed stages unconsumed, the in-order producer
-        // blocked on their slots, and a warp waiting for a later stage never reached the barrier: deadlock,
-        // seen once a slow append -- a label load queued behind the bulk copies -- put a warp 32 stages behind.)
-        uint32_t g = 0;
-        if (lane == 0) g = atomicAdd(&sm.next_stage, 1u);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        const uint32_t slot = g % kStages;
-        wait_stage_tag(&sm.meta[slot], g);
-        mbar_wait(&sm.full_bar[slot], (g / kStages) & 1u);
+        if (!landed) {
+#ifdef DAWN_SCAN_TRACE
+            unsigned long long tp0, tp1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp0));
+#endif
+            consumer_bar_sync();
+            prune<QT>(sm, kprime, tid);
+            thr = ((volatile float *)sm.thr)[my_q];
+#ifdef DAWN_SCAN_TRACE
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp1));
+            if (tid == 0) { SCAN_TRACE_ADD(9, tp1 - tp0); SCAN_TRACE_ADD(10, 1ull); }
+#endif
+            continue;  // stage g has not been consumed: wait for it again
+        }
         if (g == 0 && lane == 0) SCAN_TRACE(5);
         const uint32_t row_base = sm.meta[slot].row_base;
         const uint32_t n_stage_rows = sm.meta[slot].n_rows;
@@ -406,6 +420,7 @@ scan_topk_f16_kernel(const __half *__restrict__ corpus, const uint64_t *__restri
                 }
             }
         }
+        g += kConsumerWarps;
     }
 
     // End of this warp's stream: keep joining prunes until every consumer warp is done.
@@ -479,8 +494,6 @@ scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restri
             mbar_init(&sm.empty_bar[s], 1);
         }
         sm.done_warps = 0;
-        sm.next_stage = 0;
-        for (int st = 0; st < (int)(sizeof(sm.meta) / sizeof(sm.meta[0])); st++) sm.meta[st].stage = kNoStage;
         sm.overflow = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -564,22 +577,23 @@ scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restri
     for (int q = 0; q < QT; q++) qmask[q] = __ballot_sync(0xffffffffu, my_q == q && is_rep);
 
     float thr = ((volatile float *)sm.thr)[my_q];
+    uint32_t g = warp;
     while (true) {
-        {   // join a prune if any query's buffer reached the high-water mark (no slot is held here)
-            uint32_t c = lane < QT ? ((volatile uint32_t *)sm.cnt)[lane] : 0u;
-            if (__any_sync(0xffffffffu, c >= (uint32_t)kHighWater)) {
-                consumer_bar_sync();
-                prune<QT>(sm, kprime, tid);
-                thr = ((volatile float *)sm.thr)[my_q];
-                continue;
-            }
-        }
-        uint32_t g = 0;  // next stage by ticket (see the fp16 kernel)
-        if (lane == 0) g = atomicAdd(&sm.next_stage, 1u);
-        g = __shfl_sync(0xffffffffu, g, 0);
+        // join a prune if any query's buffer reached the high-water mark, seen here or while waiting for data
+        // (no slot is held here; see wait_stage_or_prune for why the wait must be interruptible)
         const uint32_t slot = g % kI8Stages;
-        wait_stage_tag(&sm.meta[slot], g);
-        mbar_wait(&sm.full_bar[slot], (g / kI8Stages) & 1u);
+        bool landed;
+        {
+            uint32_t c = lane < QT ? ((volatile uint32_t *)sm.cnt)[lane] : 0u;
+            landed = !__any_sync(0xffffffffu, c >= (uint32_t)kHighWater) &&
+                     wait_stage_or_prune<QT>(&sm.full_bar[slot], (g / kI8Stages) & 1u, sm.cnt, lane);
+        }
+        if (!landed) {
+            consumer_bar_sync();
+            prune<QT>(sm, kprime, tid);
+            thr = ((volatile float *)sm.thr)[my_q];
+            continue;
+        }
         const uint32_t row_base = sm.meta[slot].row_base;
         const uint32_t n_stage_rows = sm.meta[slot].n_rows;
         if (n_stage_rows == 0) break;
@@ -656,6 +670,7 @@ scan_topk_i8_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restri
                 }
             }
         }
+        g += kConsumerWarps;
     }
 
     __syncwarp();
