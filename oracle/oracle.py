@@ -432,3 +432,36 @@ def make_queries(corpus_seed: int, query_seed: int, nq: int, n_rows: int,
 def planted_rows(query_seed: int, nq: int, n_rows: int, planted_fraction: float = 0.5) -> np.ndarray:
     n_pl = int(nq * planted_fraction) if n_rows > 0 else 0
     return (np_mix64(np.arange(n_pl, dtype=np.uint64) + np.uint64(query_seed + 77)) % np.uint64(max(n_rows, 1))).astype(np.int64)
+
+
+def np_store_i8(rows: np.ndarray):
+    """numpy twin of dawn_oracle_store_i8: scale = absmax/127 (f32 division), q = roundf(x/scale) (half away
+    from zero, the reference's rounding at src/search/vector.rs:30-32), clamped to +-127."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, EM_LEN)
+    amax = np.abs(rows).max(axis=1).astype(np.float32)
+    scale = np.where(amax > 0, (amax / np.float32(127.0)).astype(np.float32), np.float32(1.0)).astype(np.float32)
+    t64 = (rows / scale[:, None]).astype(np.float32).astype(np.float64)  # the f32 quotient; +-0.5 is exact in f64
+    q = np.where(t64 >= 0, np.floor(t64 + 0.5), np.ceil(t64 - 0.5))
+    q = np.clip(q, -127, 127)
+    return q.astype(np.int8), scale
+
+
+def np_to24(v: np.ndarray) -> bytes:
+    """numpy twin of Vec::<f32>::to24 (src/search/vector.rs:74-86): ((x+1)/2 * 0x7FFFFF) as i32, low 3 bytes LE."""
+    v = np.ascontiguousarray(v, dtype=np.float32).reshape(EM_LEN)
+    t = (v.astype(np.float64) + 1.0) / 2.0 * float(0x7FFFFF)
+    x = np.where(np.isnan(t), 0.0, np.clip(np.trunc(t), -2147483648.0, 2147483647.0)).astype(np.int64)
+    x = (x & 0xFFFFFFFF).astype(np.uint32)
+    out = np.empty((EM_LEN, 3), dtype=np.uint8)
+    out[:, 0] = x & 0xFF
+    out[:, 1] = (x >> 8) & 0xFF
+    out[:, 2] = (x >> 16) & 0xFF
+    return out.tobytes()
+
+
+def np_from24(data: bytes) -> np.ndarray:
+    """numpy twin of Vec::<f32>::from24 (src/search/vector.rs:52-72) including its `v |= 0xFF` quirk."""
+    b = np.frombuffer(data, dtype=np.uint8).reshape(EM_LEN, 3).astype(np.int64)
+    v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+    v = np.where((b[:, 2] & 0x80) > 0, v | 0xFF, v)
+    return (v.astype(np.float64) / float(0x7FFFFF) * 2.0 - 1.0).astype(np.float32)

@@ -20,6 +20,30 @@ def i8_options(dawn, **kw):
     return dawn.IndexOptions(quantization=dawn.ScalarKind.I8, **kw)
 
 
+def test_i8_golden_vectors_through_the_c_abi(dawn, oracle):
+    """tests/golden/golden_v2.npz: int8 storage + search pinned by the numpy restatement (make_golden_v2.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2.npz"))
+    n = int(g["n"])
+    rows = oracle.np_synth_rows_f32(int(g["seed"]), 0, n)
+    with dawn.new_index(i8_options(dawn)) as idx:
+        idx.reserve(n)
+        idx.add_batch(g["labels"], rows)
+        for k in (1, 10, 20, 100):
+            labels, dist, counts = idx.search_batch(g["queries"], k)
+            assert (counts == k).all()
+            assert (labels == g[f"labels_k{k}"]).all()
+            assert (bits(dist) == g[f"dist_k{k}"]).all()
+        for i in range(3):  # the wire form of the same queries gives the same hits as the decoded query
+            wire = g["i24_wire"][i].tobytes()
+            assert dawn.encode_i24(g["queries"][i]) == wire
+            dec = dawn.decode_i24(wire)
+            assert (bits(dec) == g["i24_decoded"][i]).all()
+            m = idx.search_i24(wire, 10)
+            wl, wd = oracle.search_i8(*oracle.store_i8(rows), g["labels"], dec, 10)
+            assert (m.labels == wl).all() and (bits(m.distances) == bits(wd)).all()
+
+
 @pytest.mark.parametrize("n", [1, 7, 8, 9, 255, 257, 1000, 5000])
 def test_i8_search_matches_oracle(dawn, oracle, n):
     rows = oracle.np_synth_rows_f32(SEED, 0, n)

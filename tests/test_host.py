@@ -137,3 +137,11 @@ def test_library_vector_helpers_match_oracle(dawn, oracle):
         dawn.decode_i24(dawn.encode_i24(bad))  # "Embedding is not normalized"
     nan = np.full(384, np.nan, dtype=np.float32)
     assert not dawn.is_normalized(nan)
+
+
+def test_library_i24_codec_matches_golden_v2(dawn):
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2.npz"))
+    for i in range(3):
+        wire = g["i24_wire"][i].tobytes()
+        assert dawn.encode_i24(g["queries"][i]) == wire
+        assert (dawn.decode_i24(wire).view(np.uint32) == g["i24_decoded"][i]).all()

@@ -170,6 +170,30 @@ def test_golden_vectors(oracle):
             assert (bits(d) == g[f"dist_k{k}"][i]).all()
 
 
+def test_golden_v2_int8_storage_and_i24_codec(oracle):
+    """tests/golden/golden_v2.npz (numpy restatements, make_golden_v2.py) pins the C oracle's int8 storage,
+    int8 search and i24 wire codec."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2.npz"))
+    n = int(g["n"])
+    rows = oracle.np_synth_rows_f32(int(g["seed"]), 0, n)
+    q8, sc = oracle.store_i8(rows)
+    assert (q8[:3] == g["i8_head"]).all() and (sc[:3].view(np.uint32) == g["scales_head"]).all()
+    assert int(q8.astype(np.int64).sum()) == int(g["i8_checksum"])
+    assert int(sc.view(np.uint32).astype(np.uint64).sum()) == int(g["scales_checksum"])
+    q8n, scn = oracle.np_store_i8(rows)
+    assert (q8 == q8n).all() and (sc.view(np.uint32) == scn.view(np.uint32)).all()
+    for k in (1, 10, 20, 100):
+        for i, q in enumerate(g["queries"]):
+            l, d = oracle.search_i8(q8, sc, g["labels"], q, k)
+            assert (l == g[f"labels_k{k}"][i]).all() and (bits(d) == g[f"dist_k{k}"][i]).all()
+    for i in range(3):
+        wire = oracle.to24(g["queries"][i])
+        assert wire == g["i24_wire"][i].tobytes() == oracle.np_to24(g["queries"][i])
+        dec, ok = oracle.from24(wire)
+        assert ok and (bits(dec) == g["i24_decoded"][i]).all()
+        assert (bits(oracle.np_from24(wire)) == g["i24_decoded"][i]).all()
+
+
 def test_reference_invariants_on_search(oracle):
     n = 2000
     rows = oracle.np_synth_rows_f32(21, 0, n)
