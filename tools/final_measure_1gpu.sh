@@ -2,7 +2,8 @@
 # Round-end measurements on ONE B200 (every line a file under gpurun_out/final/; copied to profiles/ afterwards).
 set -u
 O=gpurun_out/final
-mkdir -p $O
+mkdir -p $O tools/bin
+[ -x tools/bin/scan_trace ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DDAWN_SCAN_TRACE -I include tools/scan_trace.cu -o tools/bin/scan_trace
 timeout 600 python bench.py                                   > $O/bench_100m_1gpu.json      2> $O/bench_100m_1gpu.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
 timeout 300 python bench.py --rows 10000000 --no-cpu-baseline --sweep 1,2,4,1:20,1:100 > $O/bench_10m_1gpu_c2.json 2> /dev/null

@@ -2,7 +2,8 @@
 # Round-end check of the final tree on ONE B200: full GPU test suite, default bench line, int8 shard, ncu evidence.
 set -u
 O=gpurun_out/final
-mkdir -p $O
+mkdir -p $O tools/bin
+[ -x tools/bin/scan_trace ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DDAWN_SCAN_TRACE -I include tools/scan_trace.cu -o tools/bin/scan_trace
 (timeout 600 python -m pytest tests -m gpu -x -q) > $O/pytest_gpu.txt 2>&1; tail -3 $O/pytest_gpu.txt
 timeout 600 python bench.py > $O/bench_100m_1gpu.json 2> $O/bench_100m_1gpu.err
 timeout 300 python bench.py --scalar i8 --rows 62500000 --batch 1 --steps 30 --warmup 5 --no-cpu-baseline > $O/bench_i8_62m5_1gpu_batch1.json 2> /dev/null
