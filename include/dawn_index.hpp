@@ -3,7 +3,7 @@
 // there is no Rust toolchain in this build image, so this is the compiled-language host side; the
 // Rust shim with the same shape is in rust/src/index/gpu_index.rs.
 //
-//   dawn::ffi::{IndexOptions, MetricKind, ScalarKind, Matches, Index, new_index}
+//   dawn::ffi::{IndexOptions, MetricKind, ScalarKind, Matches, Index, new_index, Batcher}
 //        == usearch::ffi as used at /root/reference/src/search/search_provider.rs:32-42,102,115-117,
 //           133,149,178,214,221,246,280-284 (same method names, argument meaning; C++ exceptions
 //           where the cxx bridge returned Result::Err)
@@ -47,6 +47,18 @@ inline void check(int rc) {
 inline float vector_length(const float *v) { return dawn_vector_length(v); }   // :181-183
 inline bool is_normalized(const float *v) { return dawn_is_normalized(v) != 0; }  // :185-192
 inline void normalize(std::vector<float> &v) { dawn_normalize(v.data()); }      // :194-197
+inline std::vector<std::uint8_t> to24(const std::vector<float> &v) {               // :74-86
+    if (v.size() != EM_LEN) throw Error(DAWN_ERR_INVALID, "embedding must have 384 dimensions");
+    std::vector<std::uint8_t> out(3 * EM_LEN);
+    dawn_encode_i24(v.data(), out.data());
+    return out;
+}
+inline std::vector<float> from24(const std::vector<std::uint8_t> &data) {          // :52-72 (ensure!s the norm)
+    if (data.size() != 3 * EM_LEN) throw Error(DAWN_ERR_INVALID, "i24 embedding must be 1152 bytes");
+    std::vector<float> v(EM_LEN);
+    if (dawn_decode_i24(data.data(), v.data()) != DAWN_OK) throw Error(DAWN_ERR_INVALID, "Embedding is not normalized");
+    return v;
+}
 inline float distance_cosine(const float *a, const float *b) {                   // :128-134
     float result = 0.0f;
     for (std::size_t i = 0; i < EM_LEN; i++) result += a[i] * b[i];
@@ -187,7 +199,66 @@ public:
         check(dawn_index_get(h_, label, v.data()));
         return v;
     }
+    // ---- the callers and formats either side of the path --------------------------------
+    // UdpPacket::Search{distance_limit} (src/net/udp_packets.rs:29-39): hits with distance >= limit are dropped
+    // (src/net/udp_service.rs:196-199); the limit is pushed down into the scan kernels.
+    Matches search_limit(const std::vector<float> &query, std::size_t count, float distance_limit) const {
+        if (query.size() != EM_LEN) throw Error(DAWN_ERR_INVALID, "query must have 384 dimensions");
+        Matches m;
+        m.labels.resize(count);
+        m.distances.resize(count);
+        std::size_t n = 0;
+        check(dawn_index_search_limit(h_, query.data(), count, distance_limit, m.labels.data(), m.distances.data(), &n));
+        m.labels.resize(n);
+        m.distances.resize(n);
+        return m;
+    }
+    // The peer side of a remote search: the 1152-byte i24 embedding straight off the wire (vector.rs:48-87).
+    Matches search_i24(const std::vector<std::uint8_t> &wire, std::size_t count, bool has_limit = false,
+                       float distance_limit = 0.0f) const {
+        if (wire.size() != 3 * EM_LEN) throw Error(DAWN_ERR_INVALID, "i24 embedding must be 1152 bytes");
+        Matches m;
+        m.labels.resize(count);
+        m.distances.resize(count);
+        std::size_t n = 0;
+        check(dawn_index_search_i24(h_, wire.data(), count, has_limit ? 1 : 0, distance_limit, m.labels.data(),
+                                    m.distances.data(), &n));
+        m.labels.resize(n);
+        m.distances.resize(n);
+        return m;
+    }
+    std::vector<std::uint8_t> get_i24(std::uint64_t label) const {  // GetEmbedding over UDP (udp_service.rs:254-276)
+        std::vector<std::uint8_t> v(3 * EM_LEN);
+        check(dawn_index_get_i24(h_, label, v.data()));
+        return v;
+    }
     dawn_index *handle() const { return h_; }
+};
+
+// Micro-batching front for SearchService (src/search/search_service.rs:55-104): many threads call search() with one
+// query each, a worker thread inside the library answers them in batches.  Must not outlive the index.
+class Batcher {
+    dawn_batcher *b_ = nullptr;
+
+public:
+    Batcher(const Index &index, std::size_t max_batch, std::uint32_t max_wait_us) {
+        check(dawn_batcher_create(index.handle(), max_batch, max_wait_us, &b_));
+    }
+    ~Batcher() { dawn_batcher_free(b_); }
+    Batcher(const Batcher &) = delete;
+    Batcher &operator=(const Batcher &) = delete;
+    Matches search(const std::vector<float> &query, std::size_t count) const {
+        if (query.size() != EM_LEN) throw Error(DAWN_ERR_INVALID, "query must have 384 dimensions");
+        Matches m;
+        m.labels.resize(count);
+        m.distances.resize(count);
+        std::size_t n = 0;
+        if (dawn_batcher_search(b_, query.data(), count, m.labels.data(), m.distances.data(), &n) != DAWN_OK)
+            throw Error(DAWN_ERR_INTERNAL, dawn_batcher_last_error());
+        m.labels.resize(n);
+        m.distances.resize(n);
+        return m;
+    }
 };
 
 inline std::unique_ptr<Index> new_index(const IndexOptions &o) { return std::make_unique<Index>(o); }  // :102
