@@ -2,6 +2,7 @@
 // SearchService drives its SearchProvider: ExtractedPage inserts one at a time, then
 // search_embedding per query (src/search/search_service.rs:60-181).  Used by tests/test_cpp_mirror.py.
 //   provider_demo <rows.f32> <n_rows> <queries.f32> <n_queries>   -> prints "q page_id distance_bits" lines
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -29,6 +30,32 @@ int main(int argc, char **argv) {
                 std::printf("refused code=%d msg=%s\n", e.code, e.what());
                 return 0;
             }
+        }
+        if (argc == 3 && !strcmp(argv[1], "--host-only")) {
+            // the host mirrors of vector.rs / best_results.rs need no GPU:
+            //   provider_demo --host-only <vectors.f32 (3 x 384)>  -> prints the i24 bytes (hex), the decoded bits,
+            //   the normalised bits and a BestResults run
+            auto v = read_f32(argv[2], 3 * dawn::EM_LEN);
+            for (int i = 0; i < 3; i++) {
+                std::vector<float> x(v.begin() + i * dawn::EM_LEN, v.begin() + (i + 1) * dawn::EM_LEN);
+                auto wire = dawn::to24(x);
+                std::printf("wire %d ", i);
+                for (auto b : wire) std::printf("%02x", b);
+                std::printf("\n");
+                auto back = dawn::from24(wire);
+                std::printf("back %d", i);
+                for (float f : back) { uint32_t u; std::memcpy(&u, &f, 4); std::printf(" %u", u); }
+                std::printf("\n");
+                std::printf("norm %d %d\n", i, dawn::is_normalized(x.data()) ? 1 : 0);
+            }
+            dawn::BestResults<float> best(3);  // best_results.rs:44-79
+            const float d[] = {0.5f, 0.25f, 0.75f, 0.125f, 0.25f, 0.9f};
+            for (std::size_t i = 0; i < 6; i++) best.insert(dawn::NodeReference<float>{i == 4 ? 1 : i, d[i]});
+            best.sort();
+            std::printf("best");
+            for (auto &r : best.results()) std::printf(" %zu:%g", r.id, r.distance);
+            std::printf(" worst=%g\n", best.worst_distance());
+            return 0;
         }
         if (argc != 5) return 64;
         const size_t n = std::stoul(argv[2]), nq = std::stoul(argv[4]);

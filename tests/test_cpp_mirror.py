@@ -29,6 +29,31 @@ def test_cpp_mirror_builds_and_refuses_without_gpu(demo):
     assert "refused code=-2" in r.stdout and "no CPU fallback" in r.stdout
 
 
+def test_cpp_host_mirrors_match_oracle(demo, oracle, tmp_path):
+    """to24 / from24 / is_normalized / BestResults in the C++ mirror against the oracle's restatement of
+    src/search/vector.rs:48-87,185-192 and best_results.rs:44-79 (no GPU involved)."""
+    vs = oracle.make_queries(9, 10, 3, 1000)
+    vs.tofile(tmp_path / "v.f32")
+    r = subprocess.run([demo, "--host-only", str(tmp_path / "v.f32")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    lines = r.stdout.splitlines()
+    for i in range(3):
+        wire = bytes.fromhex([l for l in lines if l.startswith(f"wire {i} ")][0].split()[2])
+        assert wire == oracle.to24(vs[i])
+        back = np.array([int(x) for x in [l for l in lines if l.startswith(f"back {i}")][0].split()[2:]], dtype=np.uint32)
+        ob, ok = oracle.from24(wire)
+        assert ok and (back == ob.view(np.uint32)).all()
+        assert f"norm {i} 1" in lines
+    # BestResults(3): ids 0..5 with id 4 re-submitted as id 1 (duplicate id is rejected), sorted ascending
+    b = oracle.BestResults(3)
+    d = [0.5, 0.25, 0.75, 0.125, 0.25, 0.9]
+    for i in range(6):
+        b.insert(1 if i == 4 else i, d[i])
+    b.sort()
+    want = "best " + " ".join(f"{i}:{dist:g}" for i, dist in b.results()) + f" worst={b.worst_distance():g}"
+    assert want in lines, (want, lines[-1])
+
+
 @pytest.mark.gpu
 def test_cpp_search_provider_matches_oracle(demo, oracle, tmp_path):
     n, nq = 3000, 6
