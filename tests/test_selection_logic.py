@@ -92,3 +92,71 @@ def test_certificate_never_holds_for_a_wrong_answer(k, kp):
             seen["uncertified_and_wrong"] += 0 if exact else 1
     # the sweep must actually exercise both outcomes, including selections the certificate rightly refused
     assert seen["certified"] > 20 and seen["uncertified"] > 20 and seen["uncertified_and_wrong"] > 0, seen
+
+
+# 3. gemm_topk.cu: rounds of tiles visited in a strided permutation; a round appends every score >= the k'-th best
+#    of all earlier rounds to a per-query log; a select keeps the best k' and publishes the new threshold.  The
+#    survivors of the last select must be the global top-k' by (score desc, row asc) whatever the order of the rows,
+#    unless the log overflowed (which the kernel flags and the host answers with the exact scan).
+def rounds_select(scores, kp, tile=256, growth=8, log_cap=2048, sequential=False):
+    n = len(scores)
+    total_tiles = -(-n // tile)
+    mult = int(total_tiles * 0.6180339887498949) | 1
+    from math import gcd
+    while mult > 1 and gcd(mult, total_tiles) != 1:
+        mult += 2
+    if total_tiles <= 2 or sequential:
+        mult = 1
+    mult %= total_tiles
+    mult = mult or 1
+    kept = np.zeros(0, dtype=np.int64)
+    thr = -np.inf
+    overflow = False
+    begin, end = 0, max(1, 1024 // tile)
+    while begin < total_tiles:
+        if end > total_tiles or end + end // 4 > total_tiles:
+            end = total_tiles
+        rows = []
+        for t in range(begin, end):
+            phys = (t * mult) % total_tiles
+            rows.append(np.arange(phys * tile, min(n, (phys + 1) * tile)))
+        rows = np.concatenate(rows)
+        passed = rows[scores[rows] >= thr]
+        if len(kept) + len(passed) > log_cap:
+            overflow = True
+            passed = passed[: log_cap - len(kept)]
+        log = np.concatenate([kept, passed])
+        order = np.lexsort((log, -scores[log].astype(np.float64)))[:kp]
+        kept = log[order]
+        thr = scores[kept[-1]] if len(kept) == kp else -np.inf
+        begin, end = end, end * growth
+    return kept, overflow
+
+
+@pytest.mark.parametrize("kp,growth", [(16, 8), (32, 8), (128, 4), (16, 32)])
+def test_rounds_with_thresholds_keep_the_global_top_kp(kp, growth):
+    rng = np.random.default_rng(kp + growth)
+    for n in (5, 1000, 1024, 70_000, 300_001):
+        scores = rng.standard_normal(n).astype(np.float32)
+        kept, overflow = rounds_select(scores, kp, growth=growth)
+        assert not overflow
+        want = np.lexsort((np.arange(n), -scores.astype(np.float64)))[:kp]
+        assert (kept == want).all(), (n, kp, growth)
+
+
+def test_adversarial_row_order_overflows_only_without_the_permutation():
+    """The near neighbours of the query all sit at the end of the corpus (pages crawled last): in stored order the
+    last round meets thousands of rows above a threshold learnt from unrelated pages and the log overflows (the
+    kernel flags the query and the host re-runs it through the exact scan); visiting the tiles in the strided
+    permutation makes every round a sample of the whole corpus and the log stays small.
+    (A corpus sorted by similarity to the query from start to end can still overflow -- whole tiles beat the
+    threshold at once -- which is what the overflow flag and the exact-scan fallback are for.)"""
+    rng = np.random.default_rng(3)
+    n, kp = 400_000, 128
+    scores = rng.standard_normal(n).astype(np.float32)
+    scores[-4000:] += np.float32(10.0)
+    _, overflow_seq = rounds_select(scores, kp, growth=4, sequential=True)
+    kept, overflow_perm = rounds_select(scores, kp, growth=4)
+    assert overflow_seq and not overflow_perm
+    want = np.lexsort((np.arange(n), -scores.astype(np.float64)))[:kp]
+    assert (kept == want).all()
