@@ -170,6 +170,12 @@ cudaError_t launch_synth_i8(uint8_t *arena, size_t dst_first_row, uint64_t seed,
                             cudaStream_t s);
 cudaError_t launch_gather_f32_i8(const uint8_t *arena, const uint32_t *rows, size_t n, float *out, cudaStream_t s);
 
+// Large batches over an int8 corpus by way of the fp16 tensor-core tiles (i8_tensor.cu).
+cudaError_t launch_dequant_i8_f16(const uint8_t *arena, size_t first_row, size_t n_rows, __half *out, cudaStream_t s);
+cudaError_t launch_gather_chunk_lists(const Cand *chunk_lists, int n_queries, int kp, uint32_t row_offset, int chunk,
+                                      int n_chunks, Cand *gathered, const uint32_t *overflow, uint32_t *overflow_any,
+                                      cudaStream_t s);
+
 struct GemmSearch {
     const __half *corpus;     // [n_rows][384] fp16
     const uint64_t *labels;   // [n_rows]

@@ -105,6 +105,16 @@ struct dawn_index {
     int64_t gemm_chunk_tiles = 0;  // 0 auto
     int64_t gemm_sequential_tiles = 0;
     int64_t gemm_growth = 0;  // 0 = automatic
+    // int8 corpora: batches of at least this many queries go through the fp16 tensor-core tiles chunk by chunk
+    // (i8_tensor.cu) instead of ceil(B/2) scan passes.  0 = off (opt-in this round).
+    int64_t i8_tensor_min_batch = 0;
+    int64_t i8_tensor_chunk_rows = 4 << 20;
+    __half *d_i8_scratch = nullptr;   // one dequantised chunk
+    size_t i8_scratch_rows = 0;
+    Cand *d_i8_lists = nullptr;       // [batch][n_chunks][k'] gathered candidate lists
+    size_t i8_lists_cap = 0;
+    uint32_t *d_i8_overflow = nullptr;  // [batch] log overflow in any chunk
+    size_t i8_overflow_cap = 0;
 
     // The search workspace (partials, counters, K3 logs) is shared by all searches on this handle:
     // a search enqueued on another stream than the previous one first waits for it.
@@ -357,6 +367,118 @@ int prepare_counters(dawn_index *idx, size_t need, cudaStream_t s) {
     return DAWN_OK;
 }
 
+// int8 corpus, large batch: chunk by chunk through the fp16 tensor-core tiles (i8_tensor.cu), then one finalize over
+// the gathered per-chunk lists with the exact int8 re-score.
+constexpr float kI8DequantSlack = 5.6e-4f;  // |q.(fp16(s x8) - s x8)| <= 2^-11 ||q|| ||s x8||, plus a larger ||x~|| in the query-rounding term
+int search_i8_tensor(dawn_index *idx, const float *d_queries, size_t batch, size_t k, int kprime, uint64_t *d_labels_out,
+                     float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags, cudaStream_t s, uint32_t *d_status_out) {
+    const int grid = idx->sm_count;
+    const int kp = kprime < 64 ? 64 : kprime;  // more slack: the certificate has to absorb the dequantisation rounding
+    const size_t n = idx->size;
+    const size_t want = (size_t)idx->i8_tensor_chunk_rows;
+    const size_t n_chunks = (n + want - 1) / want;
+    const size_t rpc = ((n + n_chunks - 1) / n_chunks + 255) / 256 * 256;  // rows per chunk, whole tiles
+    const size_t qp = (batch + 255) / 256 * 256;
+    if (rpc > idx->i8_scratch_rows) {
+        if (idx->d_i8_scratch) cudaFree(idx->d_i8_scratch);
+        idx->i8_scratch_rows = 0;
+        CK(idx, cudaMalloc(&idx->d_i8_scratch, rpc * (size_t)kRowBytesF16));
+        idx->i8_scratch_rows = rpc;
+    }
+    if (batch * n_chunks * kp > idx->i8_lists_cap) {
+        if (idx->d_i8_lists) cudaFree(idx->d_i8_lists);
+        idx->i8_lists_cap = 0;
+        CK(idx, cudaMalloc(&idx->d_i8_lists, batch * n_chunks * kp * sizeof(Cand)));
+        idx->i8_lists_cap = batch * n_chunks * kp;
+    }
+    if (batch > idx->i8_overflow_cap) {
+        if (idx->d_i8_overflow) cudaFree(idx->d_i8_overflow);
+        idx->i8_overflow_cap = 0;
+        CK(idx, cudaMalloc(&idx->d_i8_overflow, batch * sizeof(uint32_t)));
+        idx->i8_overflow_cap = batch;
+    }
+    const size_t need_ws = gemm_workspace_bytes((int)batch);
+    if (need_ws > idx->gemm_ws_cap) {
+        if (idx->d_gemm_ws) cudaFree(idx->d_gemm_ws);
+        idx->gemm_ws_cap = 0;
+        CK(idx, cudaMalloc(&idx->d_gemm_ws, need_ws));
+        idx->gemm_ws_cap = need_ws;
+    }
+    if (qp * kp > idx->partials_cap) {
+        if (idx->d_partials) cudaFree(idx->d_partials);
+        idx->partials_cap = 0;
+        CK(idx, cudaMalloc(&idx->d_partials, qp * kp * sizeof(Cand)));
+        idx->partials_cap = qp * kp;
+    }
+    {
+        int prc = prepare_counters(idx, 1, s);
+        if (prc) return prc;
+    }
+    CK(idx, cudaMemsetAsync(idx->d_i8_overflow, 0, batch * sizeof(uint32_t), s));
+    const float *eps_q = nullptr;
+    EventPair evg;
+    bool timedg = begin_event(idx, 2, s, &evg);
+    for (size_t c = 0; c < n_chunks; c++) {
+        const size_t base = c * rpc;
+        const size_t rows = n - base < rpc ? n - base : rpc;
+        CK(idx, launch_dequant_i8_f16(arena_i8(idx), base, rows, idx->d_i8_scratch, s));
+        GemmSearch gs;
+        gs.corpus = idx->d_i8_scratch;
+        gs.labels = idx->labels + base;
+        gs.n_rows = rows;
+        gs.queries = d_queries;
+        gs.n_queries = (int)batch;
+        gs.kprime = kp;
+        gs.grid = grid;
+        gs.cta_group = (int)idx->gemm_cta_group;
+        gs.chunk_tiles = (int)idx->gemm_chunk_tiles;
+        gs.sequential_tiles = (int)idx->gemm_sequential_tiles;
+        gs.growth = (int)idx->gemm_growth;
+        gs.workspace = idx->d_gemm_ws;
+        gs.final_lists = idx->d_partials;
+        gs.accum_slack = kGemmAccumSlack + kI8DequantSlack;
+        const uint32_t *overflow = nullptr;
+        int launches = 0;
+        gs.eps_out = &eps_q;
+        gs.overflow_out = &overflow;
+        gs.launches_out = &launches;
+        CK(idx, launch_gemm_search(gs, s));
+        CK(idx, launch_gather_chunk_lists(idx->d_partials, (int)batch, kp, (uint32_t)base, (int)c, (int)n_chunks, idx->d_i8_lists,
+                                          overflow, idx->d_i8_overflow, s));
+        idx->prof.gemm_batches++;
+        idx->prof.kernel_launches += launches + 2;
+    }
+    if (timedg) end_event(idx, evg, s);
+    FinalizeLaunch fl;
+    fl.corpus = idx->corpus;
+    fl.queries = d_queries;
+    fl.nq = (int)batch;
+    fl.partials = idx->d_i8_lists;
+    fl.n_lists = (int)n_chunks;
+    fl.kprime = kp;
+    fl.k = (int)k;
+    fl.eps = 0.f;
+    fl.labels_out = d_labels_out;
+    fl.distances_out = d_dist_out;
+    fl.counts_out = d_counts;
+    fl.flags_out = d_flags;
+    fl.scalar = 1;
+    fl.eps_q = eps_q;  // same queries and slack for every chunk: the last chunk's values are everybody's
+    fl.overflow = idx->d_i8_overflow;
+    fl.counters = idx->d_counters;
+    fl.n_counters = 1;
+    fl.status_out = d_status_out;
+    EventPair evf;
+    bool timedf = begin_event(idx, 1, s, &evf);
+    CK(idx, launch_finalize(fl, s));
+    if (timedf) end_event(idx, evf, s);
+    idx->prof.finalize_launches++;
+    idx->prof.kernel_launches++;
+    idx->prof.queries += batch;
+    if (idx->pending.size() > 4096) drain_events(idx);
+    return DAWN_OK;
+}
+
 // Enqueue the whole search for `batch` device-resident queries on stream `s`.
 int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, size_t k, int kprime,
                         uint64_t *d_labels_out, float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags,
@@ -381,6 +503,9 @@ int search_enqueue_impl(dawn_index *idx, const float *d_queries, size_t batch, s
                         uint64_t *d_labels_out, float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags,
                         cudaStream_t s, bool scan_only, uint32_t *d_status_out) {
     const int grid = idx->sm_count;
+    if (idx->scalar == DAWN_SCALAR_I8 && !scan_only && idx->i8_tensor_min_batch > 0 &&
+        (int64_t)batch >= idx->i8_tensor_min_batch && idx->size >= 65536 && k <= 100)
+        return search_i8_tensor(idx, d_queries, batch, k, kprime, d_labels_out, d_dist_out, d_counts, d_flags, s, d_status_out);
     if (idx->scalar == DAWN_SCALAR_I8) {
         // K4: int8 storage -> streaming dp4a scan, 1 or 2 queries per pass, exact f32 re-score
         const size_t need_ws = batch * (sizeof(I8Query) + sizeof(float)) + 256;
@@ -710,6 +835,9 @@ void dawn_index_free(dawn_index *idx) {
     cudaFreeHost(idx->h_queries);
     cudaFree(idx->d_result);
     cudaFreeHost(idx->h_result);
+    cudaFree(idx->d_i8_scratch);
+    cudaFree(idx->d_i8_lists);
+    cudaFree(idx->d_i8_overflow);
     cudaFree(idx->d_partials);
     cudaFree(idx->d_counters);
     cudaFree(idx->d_gemm_ws);
@@ -1068,6 +1196,8 @@ int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value) {
     else if (!strcmp(key, "gemm_chunk_tiles")) idx->gemm_chunk_tiles = value;
     else if (!strcmp(key, "gemm_sequential_tiles")) idx->gemm_sequential_tiles = value;
     else if (!strcmp(key, "gemm_growth")) idx->gemm_growth = value;
+    else if (!strcmp(key, "i8_tensor_min_batch")) idx->i8_tensor_min_batch = value;
+    else if (!strcmp(key, "i8_tensor_chunk_rows")) idx->i8_tensor_chunk_rows = value < 65536 ? 65536 : value;
     else return fail(DAWN_ERR_INVALID, "unknown option '%s'", key);
     return DAWN_OK;
 }
