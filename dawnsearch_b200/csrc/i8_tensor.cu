@@ -9,7 +9,9 @@
 // The rounding of x~ moves a score by at most 2^-11 * ||q|| * ||s x8|| <= 5.5e-4; the caller adds that to the
 // accumulation slack, i.e. to every eps_q the certificate uses.
 //
-// Opt-in (dawn_index_set_option "i8_tensor_min_batch"); precedent for int8 storage in the reference:
+// Used for batches of at least "i8_tensor_min_batch" queries (dawn_index_set_option, default 16) over at least 65,536 rows.
+// Measured on a B200: 62.5M rows (one shard of config C5), batch 1024: 57.4 ms (k = 10), 60.9 ms (k = 100), no
+// escalations -- the scan needs 512 passes of 3.9 ms for the same batch.  Precedent for int8 storage in the reference:
 // ScalarKind::F8 in /root/reference/examples_old/search_usearch.rs:38, distance_i8 in src/search/vector.rs:157-163.
 #include "dawn_common.cuh"
 
