@@ -51,6 +51,13 @@ def parse():
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", default="", help="extra device-resident points: 'batch[:k],...' e.g. 1,4,16:100")
+    ap.add_argument("--front", default="sharded", choices=["sharded", "multi"],
+                    help="sharded: one process per GPU (torch.distributed / NCCL, the driver's launch); multi: ONE process "
+                         "drives all --gpus through the C ABI's dawn_multi_* (NCCL all-gather inside the library)")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the pre-timing comparison with the CPU oracle")
+    ap.add_argument("--parity-rows", type=int, default=2_000_000)
+    ap.add_argument("--no-hnsw", action="store_true", help="reference arm: skip the HNSW stand-in (build takes ~1 min)")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="reference arm: wall-clock budget of the exact-scan steps")
     return ap.parse_args()
 
 
@@ -132,30 +139,94 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
-def cpu_arm(args, steps, warmup, rows_total):
+def cpu_arm(args, steps, warmup, rows_total, budget_s):
     """The reference arm / cpu_baseline: the oracle port (threaded SIMD exact scan, oracle/cpu_scan.c)
-    on the host cores, on a bounded sample of the workload, scaled linearly (a scan is O(rows))."""
+    on the host cores.  Every step scans a bounded SAMPLE of the corpus for the whole query batch; the
+    sample is sized from a probe step so that warmup + steps fit `budget_s`, and the time is scaled
+    linearly to the full corpus (a scan is O(rows))."""
     from oracle import oracle as O
 
-    sample = min(args.cpu_sample_rows, rows_total)
-    stored = O.synth_rows_f16(SEED, 0, sample)
-    qs = O.make_queries(SEED, SEED + 1, args.batch, rows_total)
     threads = O.cpu_threads()
+    qs = O.make_queries(SEED, SEED + 1, args.batch, rows_total)
+    probe_rows = min(200_000, rows_total)
+    stored = O.synth_rows_f16(SEED, 0, probe_rows)
+    O.cpu_scan_f16(stored, None, qs, args.k, threads=threads)  # page in, spin up the threads
+    t0 = time.perf_counter()
+    O.cpu_scan_f16(stored, None, qs, args.k, threads=threads)
+    per_row = (time.perf_counter() - t0) / probe_rows
+    sample = int(min(rows_total, args.cpu_sample_rows, max(50_000, budget_s / ((steps + warmup) * per_row))))
+    if sample > probe_rows:
+        stored = O.synth_rows_f16(SEED, 0, sample)
+    else:
+        sample = probe_rows
     times = []
-    for s in range(warmup + steps):
+    for s_ in range(warmup + steps):
         t0 = time.perf_counter()
         O.cpu_scan_f16(stored, None, qs, args.k, threads=threads)
         dt = time.perf_counter() - t0
-        if s >= warmup:
+        if s_ >= warmup:
             times.append(dt)
     scale = rows_total / sample
     step_s = statistics.mean(times) * scale
     return {
         "value": args.batch / step_s, "unit": "queries/s", "cores": threads, "kind": "port",
         "sample": f"{sample} of {rows_total} rows per step (oracle/cpu_scan.c, {threads} threads), "
-                  f"time scaled x{scale:.1f} (a scan is linear in rows); {steps} steps of batch {args.batch}",
-        "ms_per_step": step_s * 1e3, "sample_ms_per_step": statistics.mean(times) * 1e3,
+                  f"time scaled x{scale:.1f} (a scan is linear in rows); {steps} timed steps of batch {args.batch} after {warmup} warm-up",
+        "ms_per_step": step_s * 1e3, "sample_ms_per_step": statistics.mean(times) * 1e3, "sample_rows": sample,
     }
+
+
+def hnsw_arm(k_list=(10, 20)):
+    """The reference's KIND of index, timed live on this box's host cores: an HNSW restatement with USearch's
+    defaults (NOT USearch 0.22.3 -- that crate is not vendored and there is no cargo here; see
+    oracle/hnsw_restatement.c) over BASELINE config C1 (100k f32 vectors, single queries), one search thread
+    (the reference's model, src/bin/dawnsearch.rs:76-78) and all threads, with recall@k against the exact
+    answer -- on the isotropic synthetic corpus and on a clustered, low-intrinsic-dimension one."""
+    from oracle import oracle as O
+
+    threads = O.cpu_threads()
+    out = {"index": "HNSW restatement (NOT USearch 0.22.3): M=16, M0=32, efConstruction=128, efSearch=64, IP on f32",
+           "host_threads": threads, "corpora": {}}
+    nq = 256
+    for name, n in (("isotropic_100k", 100_000), ("clustered_50k", 50_000)):
+        if name.startswith("iso"):
+            rows = np.concatenate([O.np_synth_rows_f32(SEED, i, min(20000, n - i)) for i in range(0, n, 20000)])
+            qs = O.make_queries(SEED, SEED + 1, nq, n)
+        else:
+            rows = np.concatenate([O.np_clustered_rows_f32(SEED, i, min(10000, n - i)) for i in range(0, n, 10000)])
+            qs = O.np_clustered_rows_f32(SEED, 1_000_000_000, nq)
+        labels = np.arange(1, n + 1, dtype=np.uint64)
+        t0 = time.perf_counter()
+        h = O.Hnsw(16, 128, 64, 1)
+        h.add_batch(labels, rows)
+        build_s = time.perf_counter() - t0
+        ent = {"rows": n, "queries": nq, "build_s_one_thread": round(build_s, 1),
+               "add_us_per_vector": round(build_s / n * 1e6, 1)}
+        stored16 = rows.astype(np.float16)
+        for k in k_list:
+            truth = np.stack([O.search_f32(rows, labels, q, k)[0] for q in qs[:64]])  # exact over the f32 vectors
+            l1, _, _ = h.search_batch(qs[:64], k, 1)
+            recall = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(l1, truth)]))
+            lat = []
+            for q in qs:
+                t1 = time.perf_counter()
+                h.search_batch(q[None, :], k, 1)
+                lat.append(time.perf_counter() - t1)
+            t1 = time.perf_counter()
+            h.search_batch(qs, k, threads)
+            mt = time.perf_counter() - t1
+            ent[f"k{k}"] = {"recall_at_k": round(recall, 4), "p50_us_one_thread": round(statistics.median(lat) * 1e6, 1),
+                            "qps_one_thread": round(1.0 / statistics.mean(lat), 1),
+                            "qps_all_threads": round(nq / mt, 1)}
+        # the exact CPU scan on the same corpus, one query at a time (what "exact" costs at the reference's scale)
+        lat = []
+        for q in qs[:32]:
+            t1 = time.perf_counter()
+            O.cpu_scan_f16(stored16, labels, q[None, :], 10, threads=threads)
+            lat.append(time.perf_counter() - t1)
+        ent["cpu_exact_scan_p50_us_all_threads"] = round(statistics.median(lat) * 1e6, 1)
+        out["corpora"][name] = ent
+    return out
 
 
 def workload_name(args):
@@ -168,20 +239,22 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 6))
-    warmup = max(1, min(args.warmup, 1))
-    r = cpu_arm(args, steps, warmup, args.rows)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)  # as given: the driver compares step counts
+    r = cpu_arm(args, steps, warmup, args.rows, args.cpu_budget_s)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"],
         "unit": "queries/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 accumulate over fp16 storage", "data": "synthetic",
         "config": {"workload": workload_name(args), "rows": args.rows, "batch": args.batch, "k": args.k,
-                   "note": "reference's USearch 0.22.3 path cannot be built here (no cargo, crate not vendored); "
-                           "this arm is the CPU exact-scan port on all host threads"},
+                   "note": "the reference's USearch 0.22.3 path cannot be built here (no cargo, crate not vendored); "
+                           "`value` is the CPU exact-scan port on all host threads over a bounded sample, scaled; the "
+                           "reference's kind of (approximate) index is timed live under `hnsw_stand_in`"},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_hnsw:
+        line["hnsw_stand_in"] = hnsw_arm()
     print_json(line)
 
 
@@ -213,6 +286,8 @@ def run_ours(args):
     n_pool = min(K + W, 8)
     pool_host = [O.make_queries(SEED, SEED + 1 + i, B, args.rows, planted_fraction=0.25) for i in range(n_pool)]
     pool_dev = [torch.from_numpy(q).to(dev) for q in pool_host]
+
+    e2e_esc = [0]  # queries re-run exactly by ShardedIndex.search (N > 1)
 
     def barrier():
         if world > 1:
@@ -252,13 +327,16 @@ def run_ours(args):
         total_ms = allmax(ev[0].elapsed_time(ev[steps]))
         step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
         prof = sh.index.profile(reset=True)
+        prof["device_uncertified_all_ranks"] = allsum(prof["device_uncertified"])
         sh.index.set_profiling(False)
         return total_ms, step_ms, prof, clocks
 
     def e2e_call(q, kk):
         if world == 1:
             return sh.index.search_batch(q, kk)
-        return sh.search(q, kk)
+        r = sh.search(q, kk)
+        e2e_esc[0] += sh.last_search_escalated
+        return r
 
     def timed_e2e(queries_host, kk, steps, warm):
         for s in range(warm):
@@ -303,6 +381,61 @@ def run_ours(args):
 
     peaks = measured_peaks()
 
+    def allsum(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- parity check, BEFORE any timing: the N-rank search path against the CPU oracle -------------
+    # (oracle/ is used here as the checker only.)  A sub-corpus of <= --parity-rows rows is sharded over the
+    # same N ranks by the same rule; 64 queries go through the host path (ShardedIndex.search: local exact
+    # top-k, packed all-gather, device merge, certificate-driven re-runs), 1 query through the single-query
+    # path, and the same 64 through the device-resident pipelined path that `value` times.  Rank 0 compares
+    # labels and distance BITS with oracle.cpu_scan_f16 / search_i8.
+    parity = None
+    if not args.no_parity_check:
+        from oracle import oracle as CK  # checker only
+
+        p_rows = min(args.rows, args.parity_rows if args.scalar == "f16" else min(args.parity_rows, 200_000))
+        pf, pn = shard_range(rank, world, p_rows)
+        shp = ShardedIndex(local, max(pn, 1), quantization=0 if args.scalar == "f16" else 1)
+        shp.index.add_synthetic(SEED, pf, pn)
+        pq = O.make_queries(SEED, SEED + 99, 64, p_rows, planted_fraction=0.25)
+        got = shp.search(pq, k)
+        got1 = shp.search(pq[:1], k)
+        esc = allsum(shp.last_search_escalated)
+        d_pq = torch.from_numpy(pq).to(dev)
+        blk_dev = shp.search_device(d_pq, k, pipelined=world > 1)
+        shp.wait_results()
+        torch.cuda.synchronize()
+        from dawnsearch_b200.sharded import ResultBlock
+        dl, dd, dc = ResultBlock(64, k).views(blk_dev.cpu())
+        dev_unc = allsum(shp.index.profile()["device_uncertified"])
+        if rank == 0:
+            if args.scalar == "f16":
+                stored = CK.synth_rows_f16(SEED, 0, p_rows)
+                wl, wd, wc, _ = CK.cpu_scan_f16(stored, None, pq, k)
+            else:
+                rows32 = np.concatenate([CK.np_synth_rows_f32(SEED, i, min(20000, p_rows - i)) for i in range(0, p_rows, 20000)])
+                q8, sc = CK.store_i8(rows32)
+                lab = np.arange(1, p_rows + 1, dtype=np.uint64)
+                res = [CK.search_i8(q8, sc, lab, q, k) for q in pq]
+                wl = np.stack([r[0] for r in res])
+                wd = np.stack([r[1] for r in res])
+                wc = np.full(64, k)
+            same_host = bool((got[2] == wc).all() and (got[0] == wl).all() and (got[1].view(np.uint32) == wd.view(np.uint32)).all())
+            same_one = bool((got1[0][0] == wl[0]).all() and (got1[1][0].view(np.uint32) == wd[0].view(np.uint32)).all())
+            same_dev = bool((dl.numpy().astype(np.uint64) == wl).all() and (dd.numpy().view(np.uint32) == wd.view(np.uint32)).all())
+            parity = {"n_ranks": world, "rows": p_rows, "queries": 64, "k": k,
+                      "bit_identical": same_host and same_one and same_dev,
+                      "host_path_batch64": same_host, "host_path_single_query": same_one, "device_pipelined_path": same_dev,
+                      "escalated_to_exact_scan": int(esc), "device_path_uncertified": int(dev_unc),
+                      "checker": "oracle/cpu_scan.c dawn_cpu_scan_f16" if args.scalar == "f16" else "oracle/dawn_oracle.c dawn_oracle_search_i8"}
+            assert parity["bit_identical"], f"parity check failed: {parity}"
+        shp.close()
+        del shp
+
     # ---- latency configuration: one query per step -----------------------------------------
     # (measured BEFORE the throughput run: that one leaves the chip on its 1000 W power cap for seconds,
     #  and single-query latency is a separate workload, not a tail of it)
@@ -321,8 +454,10 @@ def run_ours(args):
     # ---- main workload -------------------------------------------------------------------
     total_ms, step_ms, prof, clocks = timed_device(pool_dev, k, K, W, sample_clocks=True)
     value = B * K / (total_ms / 1e3)
+    e2e_esc[0] = 0
     e2e_s, lat = timed_e2e(pool_host, k, K, min(W, 3))
     prof_e2e = sh.index.profile(reset=True)
+    e2e_escalated = int(allsum(prof_e2e["escalations"] + e2e_esc[0]))
 
     # sanity: a planted neighbour must come back first (a wrong kernel cannot post a number)
     planted = O.planted_rows(SEED + 1, B, args.rows, 0.25)
@@ -367,38 +502,127 @@ def run_ours(args):
                            "e2e_step_p99": lat_sorted[min(len(lat) - 1, int(0.99 * len(lat)))]},
             "e2e": {"value": B * K / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": B * DIM * 4,
                     "d2h_bytes_per_step": B * k * 12 + B * 8 + 4, "ms_per_step": e2e_s / K * 1e3},
-            "gpu_launches": int(prof["kernel_launches"]),
+            "gpu_launches": int(prof["kernel_launches"]) + (K if world > 1 else 0),  # + one merge kernel per step at N > 1
             "roofline": roofline_of(prof, B, peaks),
             "clocks": clocks,
-            "exactness": {"uncertified_queries": int(prof_e2e["uncertified"]),
-                          "escalated_to_exact_scan": int(prof_e2e["escalations"]),
-                          "note": "labels and distances bit-identical to the CPU oracle (tests/); the e2e path "
-                                  "re-runs any query whose exactness certificate fails through the f32 scan"},
+            "exactness": {"value_leg_uncertified_queries": int(prof["device_uncertified_all_ranks"]),
+                          "e2e_leg_uncertified_queries": int(prof_e2e["uncertified"]),
+                          "e2e_leg_escalated_to_exact_scan": e2e_escalated,
+                          "note": "value leg (device-resident, cannot escalate): (rank, query) results written without an "
+                                  "exactness certificate, counted on the device by every finalize launch, summed over ranks; "
+                                  "e2e leg: any query whose certificate fails on any shard is re-run through the exact f32 "
+                                  "scan before the merge (N = 1: inside dawn_index_search_batch; N > 1: ShardedIndex.search)"},
+            "parity_check": parity,
         }
-        try:  # recall of the reference's kind of index vs the exact answer (config C1), measured by
-            # tools/c1_reference_path.py on a B200 box and committed; not re-measured here (52 s build)
-            with open(os.path.join(ROOT, "profiles", "r01_c1_reference_path_hnsw_recall.json")) as f:
-                c1 = json.load(f)
-            line["reference_path_recall"] = {
-                "source": "profiles/r01_c1_reference_path_hnsw_recall.json (tools/c1_reference_path.py)",
-                "index": c1["index"], "config": c1["config"],
-                "hnsw_recall_at_10_ef64": c1["results"]["k10"]["hnsw_ef64"]["recall"],
-                "hnsw_p50_us_ef64": c1["results"]["k10"]["hnsw_ef64"]["p50_us"],
-                "exact_gpu_recall": 1.0, "exact_gpu_p50_us": c1["b200_exact_c_abi"]["p50_us"], "note": c1["note"]}
-        except Exception:
-            pass
         if batch1:
             line["batch1"] = batch1
         if sweep:
             line["batch_sweep"] = sweep
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_arm(args, steps=2, warmup=1, rows_total=args.rows)
+            r = cpu_arm(args, steps=2, warmup=1, rows_total=args.rows, budget_s=20.0)
             line["cpu_baseline"] = {kk: r[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
         print_json(line)
     sh.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_multi(args):
+    """--front multi: ONE process drives all --gpus through the C ABI (dawn_multi_*: shards, NCCL all-gather
+    and merge inside libdawn_b200.so) -- the path a one-process Rust binary would call.  Host buffers in and
+    out on every call, so every number here is end to end; `value` is the device-side share of it (CUDA events:
+    slowest shard's local search + exchange/merge on the first device)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import dawnsearch_b200 as D
+    from dawnsearch_b200 import synth as O
+
+    G, B, k, K, W = args.gpus, args.batch, args.k, args.steps, args.warmup
+    scalar = 0 if args.scalar == "f16" else 1
+    row_bytes = ROW_BYTES if args.scalar == "f16" else 388
+    parity = None
+    if not args.no_parity_check:
+        from oracle import oracle as CK  # checker only
+
+        p_rows = min(args.rows, args.parity_rows)
+        with D.MultiIndex(list(range(G)), quantization=0) as mp:
+            mp.reserve(p_rows)
+            mp.add_synthetic(SEED, 0, p_rows)
+            pq = O.make_queries(SEED, SEED + 99, 64, p_rows, planted_fraction=0.25)
+            stored = CK.synth_rows_f16(SEED, 0, p_rows)
+            wl, wd, wc, _ = CK.cpu_scan_f16(stored, None, pq, k)
+            ok = {}
+            for name, mode in (("nccl", 2), ("peer", 1)) if G > 1 else (("peer", 1),):
+                mp.set_option("exchange", mode)
+                gl, gd, gc = mp.search_batch(pq, k)
+                m1 = mp.search(pq[0], k)
+                ok[name] = bool((gc == wc).all() and (gl == wl).all() and (gd.view(np.uint32) == wd.view(np.uint32)).all()
+                                and (m1.labels == wl[0]).all())
+            parity = {"n_shards": G, "rows": p_rows, "queries": 64, "k": k, "bit_identical": all(ok.values()),
+                      "exchange_modes": ok, "stats": mp.stats(), "checker": "oracle/cpu_scan.c dawn_cpu_scan_f16"}
+            assert parity["bit_identical"], parity
+    m = D.MultiIndex(list(range(G)), quantization=scalar)
+    m.reserve(args.rows)
+    t0 = time.perf_counter()
+    m.add_synthetic(SEED, 0, args.rows)
+    fill_s = time.perf_counter() - t0
+    n_pool = min(K + W, 8)
+    pool = [O.make_queries(SEED, SEED + 1 + i, B, args.rows, planted_fraction=0.25) for i in range(n_pool)]
+
+    def timed(queries, steps, warm):
+        for s_ in range(warm):
+            m.search_batch(queries[s_ % len(queries)], k)
+        lat, dev_ms, xch_ms = [], [], []
+        t0 = time.perf_counter()
+        for s_ in range(steps):
+            t1 = time.perf_counter()
+            m.search_batch(queries[(warm + s_) % len(queries)], k)
+            lat.append((time.perf_counter() - t1) * 1e3)
+            st = m.stats()
+            dev_ms.append(st["last_search_ms"] + st["last_exchange_ms"])
+            xch_ms.append(st["last_exchange_ms"])
+        return time.perf_counter() - t0, lat, dev_ms, xch_ms
+
+    out_modes = {}
+    for name, mode in ((("nccl", 2), ("peer", 1)) if G > 1 else (("peer", 1),)):
+        m.set_option("exchange", mode)
+        q1 = [pool[0][i:i + 1] for i in range(min(B, 16))]
+        w1, l1, d1, x1 = timed(q1, max(args.latency_steps, 20), 20)
+        out_modes[name] = {"batch1_e2e_p50_ms": statistics.median(l1), "batch1_e2e_p99_ms": sorted(l1)[int(0.99 * len(l1))],
+                           "batch1_device_p50_ms": statistics.median(d1), "batch1_exchange_merge_p50_ms": statistics.median(x1)}
+    m.set_option("exchange", 0)
+    sampler = ClockSampler(0)
+    sampler.start()
+    wall, lat, dev_ms, xch_ms = timed(pool, K, W)
+    clocks = sampler.stop()
+    st = m.stats()
+    probe = m.search_batch(pool[0], k)
+    planted = O.planted_rows(SEED + 1, B, args.rows, 0.25)
+    if len(planted):
+        assert int(probe[0][0][0]) == int(planted[0]) + 1, "planted neighbour not returned first"
+    line = {
+        "metric": METRIC, "value": B * K / (sum(dev_ms) / 1e3), "unit": "queries/s", "n_gpus": G, "steps": K, "warmup": W,
+        "ms_per_step": sum(dev_ms) / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16 x f16 -> f32 (tensor cores) / f32 scan, exact f32 re-score", "data": "synthetic",
+        "config": {"workload": workload_name(args), "front": "multi: one process, dawn_multi_* C ABI, NCCL all-gather inside the library",
+                   "rows": args.rows, "rows_per_gpu": (args.rows + G - 1) // G, "batch": B, "k": k,
+                   "l2": "inputs larger than L2 (corpus shard >> 126 MB), no flush", "corpus_fill_s": round(fill_s, 3),
+                   "value_is": "device share of the call: slowest shard's local search + exchange and merge on the first device (CUDA events)"},
+        "e2e": {"value": B * K / wall, "unit": "queries/s", "h2d_bytes_per_step": B * DIM * 4 * G,
+                "d2h_bytes_per_step": B * k * 12 + B * 4 + G * B * 4, "ms_per_step": wall / K * 1e3},
+        "latency_ms": {"e2e_step_p50": statistics.median(lat), "device_step_p50": statistics.median(dev_ms),
+                       "exchange_merge_p50": statistics.median(xch_ms)},
+        "exchange_ab": out_modes, "multi_stats": st, "gpu_launches": int(st["kernel_launches"]),
+        "roofline": {"bound": "tensor" if B >= 256 else "hbm", "note": "per-kernel rooflines are reported by the default front; "
+                     "this front reports the whole call", "achieved": 2.0 * B * args.rows * DIM / (statistics.median(dev_ms) / 1e3) / 1e12 / G,
+                     "unit": "TFLOP/s per GPU (whole call)", "peak": measured_peaks()["tf_sustained"],
+                     "frac": 2.0 * B * args.rows * DIM / (statistics.median(dev_ms) / 1e3) / 1e12 / G / measured_peaks()["tf_sustained"],
+                     "traffic": None, "corpus_stream_gbps_per_gpu": args.rows / G * row_bytes / (statistics.median(dev_ms) / 1e3) / 1e9},
+        "clocks": clocks, "parity_check": parity,
+    }
+    print_json(line)
+    m.close()
 
 
 def main():
@@ -415,6 +639,8 @@ def main():
     try:
         if args.impl == "reference":
             run_reference(args)
+        elif args.front == "multi":
+            run_multi(args)
         else:
             run_ours(args)
     finally:

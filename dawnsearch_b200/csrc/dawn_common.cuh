@@ -88,6 +88,8 @@ cudaError_t launch_synth_f16(__half *dst, uint64_t seed, uint64_t first_row, siz
 // src/search/search_provider.rs:183-195, served from the device corpus).
 cudaError_t launch_gather_f32(const __half *corpus, const uint32_t *rows, size_t n, float *out,
                               cudaStream_t s);
+// labels[i] = first + i (synthetic corpora: label = row + 1, like SQLite rowids, search_provider.rs:275)
+cudaError_t launch_iota_labels(uint64_t *dst, uint64_t first, size_t n, cudaStream_t s);
 
 struct ScanLaunch {
     const __half *corpus;     // [n_rows][384] fp16
@@ -126,6 +128,8 @@ struct FinalizeLaunch {
     uint32_t *counters;     // optional: [n_counters] words (status word first) that CTA 0 zeroes for the next search
     int n_counters;
     uint32_t *status_out;   // optional: receives counters[0] (scan status) before the reset
+    float eps_scale;        // multiplies every eps: > 1 when stored rows are longer than the reference's norm gate allows
+    uint32_t *stats;        // optional device words: [0] += queries left uncertified, [1] |= scan status
 };
 // K5+K6: merge per-CTA lists, re-score candidates in the reference's order of summation
 // (src/search/vector.rs:128-134), final order and 1 - score.
@@ -191,6 +195,7 @@ struct GemmSearch {
     void *workspace;          // gemm_workspace_bytes(n_queries)
     Cand *final_lists;        // out: [ceil128(n_queries)][kprime] sorted candidates (approximate scores)
     float accum_slack;        // bound on the tensor-core accumulation error added to every eps_q
+    float limit_score;        // 1 - distance_limit (-inf = none): rows that cannot pass it never enter a candidate log
     const float **eps_out;    // out: device pointer to per-query eps
     const uint32_t **overflow_out;  // out: device pointer to per-query overflow flags
     int *launches_out;        // out: kernels launched

@@ -1,16 +1,22 @@
 // dawn_multi.cu -- the multi-GPU layer for a SINGLE-PROCESS caller (the reference binary is one
-// process, /root/reference/src/bin/dawnsearch.rs): the corpus is sharded over the GPUs of one box,
-// every GPU answers the batch from its shard, the per-shard result blocks are pushed over NVLink
-// into GPU 0's memory (peer copies: one small message per shard, the shape of the reference's
-// scatter / gather / merge across WAN peers, src/net/udp_service.rs:314-330 and
-// src/search/search_service.rs:201-277), and merged there by merge_results_kernel.
-// (The one-process-per-GPU variant of the same exchange, with an NCCL all-gather, is
-// dawnsearch_b200/sharded.py.)
+// process, /root/reference/src/bin/dawnsearch.rs:59-128): the corpus is sharded over the GPUs of one
+// box, every GPU answers the batch from its shard, then ONE NCCL all-gather over NVLink / NVSwitch
+// moves every shard's packed block of k (label, distance) pairs per query to every GPU
+// (ncclCommInitAll over the listed devices, one communicator per shard, the collective issued as one
+// group) and merge_results_kernel merges them on the first device -- the shape of the reference's
+// scatter / gather / merge across WAN peers (src/net/udp_service.rs:314-330,
+// src/search/search_service.rs:201-277).  Exchange "peer" (one cudaMemcpyPeerAsync per shard into the
+// first device's memory) is kept for handles that list one device twice (tests on a one-GPU box), where
+// NCCL cannot form a communicator, and as the A/B partner of the collective
+// (dawn_multi_set_option "exchange").
+// (The one-process-per-GPU variant of the same exchange under torch.distributed is dawnsearch_b200/sharded.py.)
 //
 // Exactness: shards return bit-exact distances, the merge orders by (distance, label), so the
 // answer equals a single index holding everything.  Queries a shard could not certify are re-run
 // on that shard through the exact scan before the merge.
+#include <atomic>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -20,6 +26,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <nccl.h>
 
 #include "../../include/dawn_index.h"
 
@@ -35,6 +42,11 @@ struct Shard {
     // per-call device buffers (grown on demand)
     float *d_q = nullptr;
     uint8_t *d_block = nullptr;
+    uint8_t *d_gather = nullptr;  // [G][block] receive buffer of the all-gather on this device
+    size_t gather_cap = 0;
+    ncclComm_t comm = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // device time of the local search
+    float search_ms = 0.f;
     uint32_t *d_flags = nullptr;
     uint32_t *h_flags = nullptr;  // pinned
     float *h_q = nullptr;         // pinned copy of the queries for this device
@@ -63,6 +75,11 @@ struct dawn_multi {
     uint8_t *h_out = nullptr;
     size_t gather_cap = 0, out_cap = 0;
     size_t next_shard = 0;  // round-robin cursor for add
+    bool nccl_ready = false;   // communicators exist (distinct devices, more than one shard)
+    int exchange = 0;          // 0 = auto (NCCL when ready), 1 = peer copies, 2 = NCCL (error if not ready)
+    cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;  // device time of exchange + merge on the first device
+    double last_search_ms = 0, last_exchange_ms = 0;
+    uint64_t searches = 0, nccl_exchanges = 0, peer_exchanges = 0, reruns = 0;
 };
 
 namespace {
@@ -143,6 +160,8 @@ int dawn_multi_create(const int *devices, size_t n_devices, uint32_t scalar, daw
             cudaError_t e = cudaSetDevice(s->device);
             if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreate(&s->ev_a);
+            if (e == cudaSuccess) e = cudaEventCreate(&s->ev_b);
             if (e != cudaSuccess) rc = cuda_fail(e, "shard setup");
         } else {
             g_multi_err = dawn_last_error();
@@ -153,6 +172,28 @@ int dawn_multi_create(const int *devices, size_t n_devices, uint32_t scalar, daw
             return rc;
         }
         s->th = std::thread(worker_loop, s);
+    }
+    {
+        cudaSetDevice(m->shards[0]->device);
+        cudaEventCreate(&m->ev_x0);
+        cudaEventCreate(&m->ev_x1);
+    }
+    // One NCCL communicator per shard, all in this process.  NCCL refuses a device listed twice;
+    // such handles (tests on a one-GPU box) keep the peer-copy exchange.
+    bool distinct = n_devices > 1;
+    for (size_t a = 0; a < n_devices && distinct; a++)
+        for (size_t b = a + 1; b < n_devices; b++)
+            if (devices[a] == devices[b]) distinct = false;
+    if (distinct && !getenv("DAWN_MULTI_NO_NCCL")) {
+        std::vector<ncclComm_t> comms(n_devices);
+        ncclResult_t nr = ncclCommInitAll(comms.data(), (int)n_devices, devices);
+        if (nr != ncclSuccess) {
+            g_multi_err = std::string("ncclCommInitAll: ") + ncclGetErrorString(nr);
+            dawn_multi_free(m);
+            return DAWN_ERR_CUDA;
+        }
+        for (size_t g = 0; g < n_devices; g++) m->shards[g]->comm = comms[g];
+        m->nccl_ready = true;
     }
     *out = m;
     return DAWN_OK;
@@ -170,6 +211,10 @@ void dawn_multi_free(dawn_multi *m) {
             s->th.join();
         }
         cudaSetDevice(s->device);
+        if (s->comm) ncclCommDestroy(s->comm);
+        if (s->ev_a) cudaEventDestroy(s->ev_a);
+        if (s->ev_b) cudaEventDestroy(s->ev_b);
+        cudaFree(s->d_gather);
         cudaFree(s->d_q);
         cudaFree(s->d_block);
         cudaFree(s->d_flags);
@@ -181,6 +226,8 @@ void dawn_multi_free(dawn_multi *m) {
         delete s;
     }
     if (!m->shards.empty()) cudaSetDevice(m->shards[0]->device);
+    if (m->ev_x0) cudaEventDestroy(m->ev_x0);
+    if (m->ev_x1) cudaEventDestroy(m->ev_x1);
     cudaFree(m->d_gather);
     cudaFree(m->d_out);
     cudaFreeHost(m->h_out);
@@ -288,10 +335,15 @@ int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, s
     const size_t G = m->shards.size();
     const size_t bb = block_bytes(batch, k);
     const size_t off_d = batch * k * 8, off_c = off_d + batch * k * 4;
+    if (m->exchange == 2 && !m->nccl_ready) {
+        g_multi_err = "exchange = nccl requested but no communicator exists (one shard, or a device listed twice)";
+        return DAWN_ERR_INVALID;
+    }
+    const bool use_nccl = m->nccl_ready && m->exchange != 1;
     Shard *s0 = m->shards[0];
     cudaError_t e = cudaSetDevice(s0->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    if (G * bb > m->gather_cap) {
+    if (!use_nccl && G * bb > m->gather_cap) {
         cudaFree(m->d_gather);
         m->gather_cap = 0;
         if ((e = cudaMalloc(&m->d_gather, G * bb)) != cudaSuccess) return cuda_fail(e, "cudaMalloc gather");
@@ -305,11 +357,13 @@ int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, s
         if ((e = cudaMallocHost(&m->h_out, bb)) != cudaSuccess) return cuda_fail(e, "cudaMallocHost out");
         m->out_cap = bb;
     }
-    uint8_t *d_gather = m->d_gather;
+    uint8_t *d_gather_peer = m->d_gather;
     const int dev0 = s0->device;
+    std::atomic<uint64_t> reruns{0};
 
-    // every shard: H2D queries, local exact top-k into a packed block, push the block to GPU 0
-    int rc = run_all(m, [=](Shard *s, size_t g) -> int {
+    // every shard: H2D queries, local exact top-k into a packed block; then either its peer copy into the
+    // first device's gather buffer, or nothing (the all-gather is issued for all shards as one group below)
+    int rc = run_all(m, [=, &reruns](Shard *s, size_t g) -> int {
         cudaError_t ce;
         if (batch > s->q_cap) {
             cudaFree(s->d_q);
@@ -330,17 +384,26 @@ int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, s
             if ((ce = cudaMalloc(&s->d_block, bb)) != cudaSuccess) return cuda_fail(ce, "cudaMalloc block");
             s->block_cap = bb;
         }
+        if (use_nccl && G * bb > s->gather_cap) {
+            cudaFree(s->d_gather);
+            s->gather_cap = 0;
+            if ((ce = cudaMalloc(&s->d_gather, G * bb)) != cudaSuccess) return cuda_fail(ce, "cudaMalloc gather");
+            s->gather_cap = G * bb;
+        }
         memcpy(s->h_q, queries, batch * DAWN_DIMENSIONS * sizeof(float));
         if ((ce = cudaMemcpyAsync(s->d_q, s->h_q, batch * DAWN_DIMENSIONS * sizeof(float), cudaMemcpyHostToDevice, s->stream)) != cudaSuccess)
             return cuda_fail(ce, "H2D queries");
         if ((ce = cudaMemsetAsync(s->d_block, 0, bb, s->stream)) != cudaSuccess) return cuda_fail(ce, "memset block");
+        cudaEventRecord(s->ev_a, s->stream);
         int r = dawn_index_search_device(s->idx, s->d_q, batch, k, reinterpret_cast<uint64_t *>(s->d_block),
                                          reinterpret_cast<float *>(s->d_block + off_d),
                                          reinterpret_cast<uint32_t *>(s->d_block + off_c), s->d_flags, s->stream);
         if (r) return r;
+        cudaEventRecord(s->ev_b, s->stream);
         if ((ce = cudaMemcpyAsync(s->h_flags, s->d_flags, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess)
             return cuda_fail(ce, "D2H flags");
         if ((ce = cudaStreamSynchronize(s->stream)) != cudaSuccess) return cuda_fail(ce, "shard sync");
+        cudaEventElapsedTime(&s->search_ms, s->ev_a, s->ev_b);
         // queries this shard could not certify: exact re-run through the host API, patched into the block
         if (dawn_index_size(s->idx) > 0) {
             std::vector<uint64_t> l(k);
@@ -350,6 +413,7 @@ int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, s
                 size_t cnt = 0;
                 r = dawn_index_search(s->idx, queries + b * DAWN_DIMENSIONS, k, l.data(), d.data(), &cnt);
                 if (r) return r;
+                reruns++;
                 uint32_t c32 = (uint32_t)cnt;
                 cudaMemcpyAsync(s->d_block + b * k * 8, l.data(), cnt * 8, cudaMemcpyHostToDevice, s->stream);
                 cudaMemcpyAsync(s->d_block + off_d + b * k * 4, d.data(), cnt * 4, cudaMemcpyHostToDevice, s->stream);
@@ -357,32 +421,109 @@ int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, s
                 if ((ce = cudaStreamSynchronize(s->stream)) != cudaSuccess) return cuda_fail(ce, "patch sync");
             }
         }
-        // one message per shard over NVLink into GPU 0's gather buffer
-        if ((ce = cudaMemcpyPeerAsync(d_gather + g * bb, dev0, s->d_block, s->device, bb, s->stream)) != cudaSuccess)
-            return cuda_fail(ce, "peer copy");
-        if ((ce = cudaStreamSynchronize(s->stream)) != cudaSuccess) return cuda_fail(ce, "peer sync");
+        if (!use_nccl) {
+            // one message per shard over NVLink into the first device's gather buffer
+            if ((ce = cudaMemcpyPeerAsync(d_gather_peer + g * bb, dev0, s->d_block, s->device, bb, s->stream)) != cudaSuccess)
+                return cuda_fail(ce, "peer copy");
+            if ((ce = cudaStreamSynchronize(s->stream)) != cudaSuccess) return cuda_fail(ce, "peer sync");
+        }
         return DAWN_OK;
     });
     if (rc) return rc;
+    m->reruns += reruns;
+    m->searches++;
+    double smax = 0;
+    for (Shard *s : m->shards) smax = s->search_ms > smax ? s->search_ms : smax;
+    m->last_search_ms = smax;
 
-    // device-side merge on GPU 0, then one D2H of the merged block
     if ((e = cudaSetDevice(dev0)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    rc = dawn_merge_results_device(dev0, reinterpret_cast<uint64_t *>(d_gather), reinterpret_cast<float *>(d_gather + off_d),
-                                   reinterpret_cast<uint32_t *>(d_gather + off_c), G, bb, batch, k,
+    cudaEventRecord(m->ev_x0, s0->stream);
+    const uint8_t *d_gather = d_gather_peer;
+    if (use_nccl) {
+        // THE exchange: one all-gather of the packed blocks, issued for every shard's communicator as one group
+        // (every shard's stream is idle here, so the collective starts at once on all GPUs)
+        ncclResult_t nr = ncclGroupStart();
+        for (size_t g = 0; g < G && nr == ncclSuccess; g++) {
+            Shard *s = m->shards[g];
+            nr = ncclAllGather(s->d_block, s->d_gather, bb, ncclUint8, s->comm, s->stream);
+        }
+        ncclResult_t ne = ncclGroupEnd();
+        if (nr == ncclSuccess) nr = ne;
+        if (nr != ncclSuccess) {
+            g_multi_err = std::string("ncclAllGather: ") + ncclGetErrorString(nr);
+            return DAWN_ERR_CUDA;
+        }
+        m->nccl_exchanges++;
+        d_gather = s0->d_gather;
+        cudaSetDevice(dev0);
+    } else {
+        m->peer_exchanges++;
+    }
+    // device-side merge on the first device, then one D2H of the merged block
+    rc = dawn_merge_results_device(dev0, reinterpret_cast<const uint64_t *>(d_gather), reinterpret_cast<const float *>(d_gather + off_d),
+                                   reinterpret_cast<const uint32_t *>(d_gather + off_c), G, bb, batch, k,
                                    reinterpret_cast<uint64_t *>(m->d_out), reinterpret_cast<float *>(m->d_out + off_d),
                                    reinterpret_cast<uint32_t *>(m->d_out + off_c), s0->stream);
     if (rc) {
         g_multi_err = dawn_last_error();
         return rc;
     }
+    cudaEventRecord(m->ev_x1, s0->stream);
     if ((e = cudaMemcpyAsync(m->h_out, m->d_out, bb, cudaMemcpyDeviceToHost, s0->stream)) != cudaSuccess) return cuda_fail(e, "D2H out");
     if ((e = cudaStreamSynchronize(s0->stream)) != cudaSuccess) return cuda_fail(e, "final sync");
+    if (use_nccl)  // the other shards' receive buffers are reused by the next call
+        for (size_t g = 1; g < G; g++) {
+            cudaSetDevice(m->shards[g]->device);
+            if ((e = cudaStreamSynchronize(m->shards[g]->stream)) != cudaSuccess) return cuda_fail(e, "all-gather sync");
+        }
+    float xms = 0.f;
+    cudaEventElapsedTime(&xms, m->ev_x0, m->ev_x1);
+    m->last_exchange_ms = xms;
     const uint32_t *cnt = reinterpret_cast<const uint32_t *>(m->h_out + off_c);
     for (size_t b = 0; b < batch; b++) {
         counts_out[b] = cnt[b];
         memcpy(labels_out + b * k, m->h_out + b * k * 8, cnt[b] * 8);
         memcpy(distances_out + b * k, m->h_out + off_d + b * k * 4, cnt[b] * 4);
     }
+    return DAWN_OK;
+}
+
+// "exchange": 0 = auto (NCCL all-gather when communicators exist), 1 = peer copies, 2 = NCCL or fail.
+int dawn_multi_set_option(dawn_multi *m, const char *key, int64_t value) {
+    if (!m || !key) return DAWN_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (!strcmp(key, "exchange")) {
+        if (value < 0 || value > 2) return DAWN_ERR_INVALID;
+        m->exchange = (int)value;
+        return DAWN_OK;
+    }
+    // everything else is a per-shard index option
+    for (Shard *s : m->shards) {
+        int rc = dawn_index_set_option(s->idx, key, value);
+        if (rc) {
+            g_multi_err = dawn_last_error();
+            return rc;
+        }
+    }
+    return DAWN_OK;
+}
+
+int dawn_multi_get_stats(dawn_multi *m, dawn_multi_stats *out) {
+    if (!m || !out) return DAWN_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(m->mu);
+    out->searches = m->searches;
+    out->nccl_exchanges = m->nccl_exchanges;
+    out->peer_exchanges = m->peer_exchanges;
+    out->exact_reruns = m->reruns;
+    out->last_search_ms = m->last_search_ms;
+    out->last_exchange_ms = m->last_exchange_ms;
+    out->nccl_ready = m->nccl_ready ? 1 : 0;
+    out->kernel_launches = 0;
+    for (Shard *s : m->shards) {
+        dawn_profile p{};
+        if (dawn_index_get_profile(s->idx, &p, 0) == DAWN_OK) out->kernel_launches += p.kernel_launches;
+    }
+    out->kernel_launches += m->searches + m->nccl_exchanges * m->shards.size();  // merge kernel + NCCL's kernels
     return DAWN_OK;
 }
 

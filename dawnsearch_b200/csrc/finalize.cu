@@ -46,6 +46,7 @@ struct FinSmem {
     float kth_dist;
     uint32_t n_surv;
     float bound;
+    float q_norm2;
     alignas(16) Cand s[1];  // kFinCapEntries entries when merging, kp entries for a single list
 };
 constexpr int kRowStrideF16 = kRowBytesF16 + 16;  // staged candidate rows: +16 B so that thread-per-row reads are conflict free
@@ -203,7 +204,8 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
                 uint64_t *__restrict__ labels_out, float *__restrict__ distances_out,
                 uint32_t *__restrict__ counts_out, uint32_t *__restrict__ flags_out,
                 const float *__restrict__ eps_q, const uint32_t *__restrict__ overflow, int scalar,
-                uint32_t *__restrict__ counters, int n_counters, uint32_t *__restrict__ status_out) {
+                uint32_t *__restrict__ counters, int n_counters, uint32_t *__restrict__ status_out, float eps_scale,
+                uint32_t *__restrict__ stats) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FinSmem &sm = *reinterpret_cast<FinSmem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -307,6 +309,14 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
         const uint32_t w = __reduce_min_sync(0xffffffffu, float_to_ordered(my_scan));
         if ((tid & 31) == 0) sm.warp_min[tid >> 5] = w;
     }
+    if (tid < 32) {  // |q|^2: every eps below is proportional to |q| |x|
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < kDim / 32; j++) a = fmaf(sm.q[tid + 32 * j], sm.q[tid + 32 * j], a);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (tid == 0) sm.q_norm2 = a;
+    }
     const int n_valid = __syncthreads_count(valid ? 1 : 0);
 
     // ---- final order: distance asc, label asc, row asc (rank counting over <= 128 entries).
@@ -328,7 +338,9 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
             // A row outside the candidate set has scan score <= scan_min, hence exact score
             // <= scan_min + eps and distance >= 1 - (scan_min + eps); it cannot displace or tie
             // the k-th result if that bound is strictly above the k-th distance.
-            const float e = eps_q ? eps_q[qi] : eps;
+            // the eps constants assume |q|, |x| inside the reference's gate (< 1.01); longer vectors scale them
+            const float qn = sqrtf(sm.q_norm2);
+            const float e = (eps_q ? eps_q[qi] : eps) * eps_scale * (qn > 1.01f ? qn * (1.001f / 1.01f) : 1.0f);
             uint32_t wmin = sm.warp_min[0];
             for (int w = 1; w < (kp + 31) / 32; w++) wmin = min(wmin, sm.warp_min[w]);
             const float scan_min = ordered_to_float(wmin);  // weakest kept candidate (lists need not be sorted)
@@ -337,11 +349,13 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
         }
         if (overflow && overflow[qi]) certified = false;  // candidates were lost: cannot certify
         flags_out[qi] = certified ? 1u : 0u;
+        if (!certified && stats) atomicAdd(&stats[0], 1u);
     }
     FIN_TRACE(7);
     // the last kernel of a search leaves the chunk counters / status word clean for the next one
     if (blockIdx.x == 0 && counters) {
         if (tid == 0 && status_out) *status_out = counters[0];
+        if (tid == 0 && stats && counters[0]) atomicOr(&stats[1], counters[0]);
         __syncthreads();
         for (int i = tid; i < n_counters; i += nthr) counters[i] = 0u;
     }
@@ -365,7 +379,8 @@ cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s) {
     }
     finalize_kernel<<<p.nq, p.n_lists == 1 ? kFinThreadsSingle : kFinThreads, smem, s>>>(
         p.corpus, p.queries, p.partials, p.n_lists, p.kprime, p.k, p.eps, p.labels_out, p.distances_out, p.counts_out,
-        p.flags_out, p.eps_q, p.overflow, p.scalar, p.counters, p.n_counters, p.status_out);
+        p.flags_out, p.eps_q, p.overflow, p.scalar, p.counters, p.n_counters, p.status_out,
+        p.eps_scale > 0.f ? p.eps_scale : 1.0f, p.stats);
     return cudaGetLastError();
 }
 

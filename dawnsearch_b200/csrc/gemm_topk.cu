@@ -490,11 +490,11 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float *__restri
     for (int off = 16; off > 0; off >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, off);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = err2;
     __syncthreads();
-    if (threadIdx.x == 0 && q < n_queries) {
+    if (threadIdx.x == 0) {
         float s = red[0] + red[1] + red[2] + red[3];
         // |sum (q_i - q16_i) x_i| <= ||q - q16|| * ||x||, stored rows have norm < 1.011 (the reference's
         // gate is 1.01, vector.rs:185-192, plus fp16 rounding); 1.02 also covers the f32 rounding here.
-        eps_q[q] = sqrtf(s) * 1.02f + accum_slack;
+        eps_q[q] = q < n_queries ? sqrtf(s) * 1.02f + accum_slack : 0.f;
     }
     (void)n_padded;
 }
@@ -510,7 +510,8 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(uint2 *__restr
                                                                   float *__restrict__ thr_g,
                                                                   uint32_t *__restrict__ overflow_g, int log_cap, int kp,
                                                                   const uint64_t *__restrict__ labels,
-                                                                  Cand *__restrict__ final_lists) {
+                                                                  Cand *__restrict__ final_lists,
+                                                                  const float *__restrict__ eps_q, float limit_score) {
     __shared__ unsigned long long keys[kSelCap];
     __shared__ unsigned long long s_prefix;
     __shared__ uint32_t hist[256];
@@ -595,7 +596,11 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(uint2 *__restr
         for (int i = keep + tid; i < kp; i += kSelThreads) final_lists[(size_t)q * kp + i] = empty_cand();
     if (tid == 0) {
         cnt_g[q] = (uint32_t)keep;
-        thr_g[q] = n >= kp ? ordered_to_float((uint32_t)(K >> 32)) : __int_as_float(0xff800000);
+        float thr = n >= kp ? ordered_to_float((uint32_t)(K >> 32)) : __int_as_float(0xff800000);
+        // distance_limit pushed down (udp_packets.rs:29-39): a row whose fp16-query score is below
+        // limit_score - eps_q has an exact distance above the limit and would be dropped by the caller anyway
+        if (limit_score > __int_as_float(0xff800000)) thr = fmaxf(thr, limit_score - eps_q[q] - 1e-6f);
+        thr_g[q] = thr;
         if (cnt > (uint32_t)log_cap) overflow_g[q] = 1u;
     }
 }
@@ -706,7 +711,8 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
     prep_queries_kernel<<<qp, 128, 0, s>>>(p.queries, p.n_queries, qp, q16, eps_q, p.accum_slack);
     {
         // -inf thresholds: written by a select pass over empty logs (cnt == 0 -> thr = -inf)
-        select_topk_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, thr, overflow, kSelCap, p.kprime, p.labels, nullptr);
+        select_topk_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, thr, overflow, kSelCap, p.kprime, p.labels, nullptr, eps_q,
+                                                      p.limit_score);
     }
     int launches = 2;
     // rounds of rows: [0,1024), then x`growth` each time ((growth-1)*k' survivors per query per
@@ -751,7 +757,7 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         const bool last = end >= total_tiles;
         select_topk_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, thr, overflow, kSelCap, p.kprime, p.labels,
-                                                      last ? p.final_lists : nullptr);
+                                                      last ? p.final_lists : nullptr, eps_q, p.limit_score);
         launches += 2;
         begin = end;
         end = end * growth;

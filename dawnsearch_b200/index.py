@@ -71,10 +71,29 @@ class Profile(C.Structure):
         ("kernel_launches", C.c_uint64),
         ("gemm_batches", C.c_uint64),
         ("gemm_ms", C.c_double),
+        ("device_uncertified", C.c_uint64),
+        ("device_status", C.c_uint64),
     ]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class MultiStats(C.Structure):
+    _fields_ = [
+        ("searches", C.c_uint64),
+        ("nccl_exchanges", C.c_uint64),
+        ("peer_exchanges", C.c_uint64),
+        ("exact_reruns", C.c_uint64),
+        ("kernel_launches", C.c_uint64),
+        ("last_search_ms", C.c_double),
+        ("last_exchange_ms", C.c_double),
+        ("nccl_ready", C.c_uint32),
+        ("reserved_", C.c_uint32),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved_"}
 
 
 @dataclass
@@ -144,6 +163,8 @@ def load_library() -> C.CDLL:
     L.dawn_encode_i24.restype = None
     L.dawn_decode_i24.argtypes = [_vp, _vp]
     L.dawn_index_search_limit.argtypes = [_vp, _vp, C.c_size_t, C.c_float, _vp, _vp, _vp]
+    L.dawn_index_search_batch_limit.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, C.c_float, _vp, _vp, _vp]
+    L.dawn_index_verify.argtypes = [_vp, _vp, _vp, _vp]
     L.dawn_index_search_i24.argtypes = [_vp, _vp, C.c_size_t, C.c_int, C.c_float, _vp, _vp, _vp]
     L.dawn_index_get_i24.argtypes = [_vp, C.c_uint64, _vp]
     L.dawn_index_add_page_entries.argtypes = [_vp, _vp, C.c_size_t, C.c_uint64, _vp]
@@ -166,6 +187,8 @@ def load_library() -> C.CDLL:
         getattr(L, name).argtypes = [_vp]
         getattr(L, name).restype = C.c_size_t
     L.dawn_multi_last_error.restype = C.c_char_p
+    L.dawn_multi_set_option.argtypes = [_vp, C.c_char_p, C.c_int64]
+    L.dawn_multi_get_stats.argtypes = [_vp, C.POINTER(MultiStats)]
     _lib = L
     return L
 
@@ -282,6 +305,24 @@ class Index:
         _check(self._L.dawn_index_search_limit(self._h, _ptr(q), count, distance_limit, _ptr(labels), _ptr(dist),
                                                C.byref(n)))
         return Matches(labels[: n.value].copy(), dist[: n.value].copy())
+
+    def search_batch_limit(self, queries, count: int, distance_limit: float):
+        """Batch form of search_limit (one limit for every query)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, EM_LEN)
+        b = q.shape[0]
+        labels = np.zeros((b, max(count, 1)), dtype=np.uint64)
+        dist = np.zeros((b, max(count, 1)), dtype=np.float32)
+        counts = np.zeros(b, dtype=np.uint64)
+        _check(self._L.dawn_index_search_batch_limit(self._h, _ptr(q), b, count, distance_limit, _ptr(labels),
+                                                     _ptr(dist), _ptr(counts)))
+        return labels, dist, counts.astype(np.int64)
+
+    def verify(self) -> dict:
+        """SearchProvider::verify over the device corpus (search_provider.rs:289-327): norm gate on every stored row."""
+        bad = C.c_size_t(0)
+        lo, hi = C.c_float(0), C.c_float(0)
+        _check(self._L.dawn_index_verify(self._h, C.byref(bad), C.byref(lo), C.byref(hi)))
+        return {"bad_rows": int(bad.value), "min_norm": float(lo.value), "max_norm": float(hi.value)}
 
     def search_i24(self, query1152: bytes, count: int, distance_limit=None) -> Matches:
         """The peer side of UdpPacket::Search: raw i24 query bytes, optional distance_limit."""
@@ -470,6 +511,15 @@ class MultiIndex:
 
     def shards(self) -> int:
         return int(self._L.dawn_multi_shards(self._h))
+
+    def set_option(self, key: str, value: int) -> None:
+        """'exchange': 0 auto, 1 peer copies, 2 NCCL all-gather; other keys go to every shard's index."""
+        self._check(self._L.dawn_multi_set_option(self._h, key.encode(), int(value)))
+
+    def stats(self) -> dict:
+        st = MultiStats()
+        self._check(self._L.dawn_multi_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
 
 
 def new_index(options: IndexOptions | None = None) -> Index:

@@ -31,13 +31,16 @@ def shard_range(rank: int, world: int, rows: int):
 
 class ResultBlock:
     """One shard's answer for a batch, packed so that it crosses NVLink as ONE message:
-    [batch*k u64 labels][batch*k f32 distances][batch u32 counts], padded to 16 bytes."""
+    [batch*k u64 labels][batch*k f32 distances][batch u32 counts][batch u32 flags], padded to 16 bytes.
+    flags bit0 = this shard's exactness certificate held for the query; travelling with the block lets
+    every rank see, without an extra exchange, whether any shard has to re-run a query exactly."""
 
     def __init__(self, batch: int, k: int):
         self.batch, self.k = batch, k
         self.off_dist = batch * k * 8
         self.off_counts = self.off_dist + batch * k * 4
-        self.nbytes = (self.off_counts + batch * 4 + 15) // 16 * 16
+        self.off_flags = self.off_counts + batch * 4
+        self.nbytes = (self.off_flags + batch * 4 + 15) // 16 * 16
 
     def views(self, buf: torch.Tensor):
         """(labels int64 [B,k], distances f32 [B,k], counts int32 [B]) aliasing a uint8 buffer."""
@@ -46,10 +49,23 @@ class ResultBlock:
                 buf[self.off_dist: self.off_counts].view(torch.float32).view(b, k),
                 buf[self.off_counts: self.off_counts + b * 4].view(torch.int32))
 
+    def flags(self, buf: torch.Tensor):
+        """int32 [B] view of the certificate flags of one block, or [world, B] of a gathered buffer."""
+        b = self.batch
+        if buf.dim() == 2:
+            return buf[:, self.off_flags: self.off_flags + b * 4].contiguous().view(torch.int32).view(buf.shape[0], b)
+        return buf[self.off_flags: self.off_flags + b * 4].view(torch.int32)
+
 
 def all_gather_blocks(local: torch.Tensor, gathered: torch.Tensor, group=None):
     """The one exchange step of a sharded search: [nbytes] uint8 per rank -> [world, nbytes] on
-    every rank.  Backend-agnostic (NCCL on the GPUs, gloo in the CPU tests)."""
+    every rank.  NCCL on the GPUs; gloo in the CPU tests, and -- staged through the host -- when several
+    ranks share one GPU (NCCL refuses that; used to test the sharded logic on a one-GPU box)."""
+    if local.is_cuda and dist.get_backend(group) == "gloo":
+        g = torch.empty(gathered.shape, dtype=torch.uint8)
+        dist.all_gather_into_tensor(g.view(-1), local.cpu(), group=group)
+        gathered.copy_(g)
+        return
     dist.all_gather_into_tensor(gathered.view(-1), local, group=group)
 
 
@@ -66,6 +82,7 @@ class ShardedIndex:
         self._ws = {}
         self._side = None
         self._last_merged = None
+        self.last_search_escalated = 0  # queries this rank re-ran exactly in the last search() call
 
     def close(self):
         self.index.close()
@@ -80,11 +97,11 @@ class ShardedIndex:
                 "blk": blk,
                 "q": torch.empty((batch, EM_LEN), dtype=torch.float32, device=d),
                 "local": torch.zeros(blk.nbytes, dtype=torch.uint8, device=d),
-                "flags": torch.empty(batch, dtype=torch.int32, device=d),
                 "gathered": torch.zeros((self.world, blk.nbytes), dtype=torch.uint8, device=d),
                 "out": torch.zeros(blk.nbytes, dtype=torch.uint8, device=d),
                 "h_q": torch.empty((batch, EM_LEN), dtype=torch.float32).pin_memory(),
                 "h_out": torch.empty(blk.nbytes, dtype=torch.uint8).pin_memory(),
+                "h_flags": torch.empty((self.world, batch), dtype=torch.int32).pin_memory(),
             }
             self._ws[key] = ws
         return ws
@@ -108,12 +125,12 @@ class ShardedIndex:
         if self.world == 1:
             base = ws["local"].data_ptr()
             self.index.search_device(d_queries.data_ptr(), batch, k, base, base + blk.off_dist, base + blk.off_counts,
-                                     ws["flags"].data_ptr(), stream)
+                                     base + blk.off_flags, stream)
             return ws["local"]
         if not pipelined:
             base = ws["local"].data_ptr()
             self.index.search_device(d_queries.data_ptr(), batch, k, base, base + blk.off_dist, base + blk.off_counts,
-                                     ws["flags"].data_ptr(), stream)
+                                     base + blk.off_flags, stream)
             all_gather_blocks(ws["local"], ws["gathered"], self.group)
             g, o = ws["gathered"].data_ptr(), ws["out"].data_ptr()
             merge_results_device(self.device, g, g + blk.off_dist, g + blk.off_counts, self.world, batch, k,
@@ -139,7 +156,7 @@ class ShardedIndex:
             main.wait_event(pp["merged"][p])
         base = pp["local"][p].data_ptr()
         self.index.search_device(d_queries.data_ptr(), batch, k, base, base + blk.off_dist, base + blk.off_counts,
-                                 ws["flags"].data_ptr(), stream)
+                                 base + blk.off_flags, stream)
         pp["searched"][p].record(main)
         side = self._side
         side.wait_event(pp["searched"][p])
@@ -159,16 +176,58 @@ class ShardedIndex:
         if self._last_merged is not None:
             torch.cuda.current_stream(self.tdev).wait_event(self._last_merged)
 
+    def _exchange(self, ws, k: int):
+        """all-gather of ws["local"] + merge into ws["out"] on the current stream."""
+        blk: ResultBlock = ws["blk"]
+        main = torch.cuda.current_stream(self.tdev)
+        stream = main.cuda_stream or 1
+        all_gather_blocks(ws["local"], ws["gathered"], self.group)
+        g, o = ws["gathered"].data_ptr(), ws["out"].data_ptr()
+        merge_results_device(self.device, g, g + blk.off_dist, g + blk.off_counts, self.world, blk.batch, k,
+                             o, o + blk.off_dist, o + blk.off_counts, stream, list_stride_bytes=blk.nbytes)
+
     def search(self, queries: np.ndarray, k: int):
-        """Host queries in, host results out (every rank gets the full merged answer)."""
+        """Host queries in, host results out (every rank gets the full merged answer).
+
+        Exactness across shards: a shard whose certificate failed for a query (near-ties deeper than the
+        candidate slack, or a candidate-log overflow on the tensor-core path) re-runs that query through
+        the host API -- which escalates to the exact scan -- patches its block, and the exchange + merge
+        are repeated.  The flags ride in the gathered blocks, so all ranks take that decision together
+        and the common case costs no extra synchronisation."""
         q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, EM_LEN)
         batch = q.shape[0]
         ws = self._workspace(batch, k)
+        blk: ResultBlock = ws["blk"]
+        self.last_search_escalated = 0
         with torch.cuda.device(self.tdev):
+            main = torch.cuda.current_stream(self.tdev)
             ws["h_q"].copy_(torch.from_numpy(q))
             ws["q"].copy_(ws["h_q"], non_blocking=True)
             out = self.search_device(ws["q"], k)
             ws["h_out"].copy_(out, non_blocking=True)
-            torch.cuda.current_stream(self.tdev).synchronize()
-        labels, dists, counts = ws["blk"].views(ws["h_out"])
+            if self.world > 1:
+                ws["h_flags"].copy_(blk.flags(ws["gathered"]), non_blocking=True)
+            else:
+                ws["h_flags"].copy_(blk.flags(ws["local"]).view(1, batch), non_blocking=True)
+            main.synchronize()
+            flags = ws["h_flags"].numpy()
+            if (flags & 1).min() == 0:  # same data on every rank -> same decision on every rank
+                mine = np.nonzero((flags[self.rank] & 1) == 0)[0]
+                if len(mine):
+                    rl, rd, rc = self.index.search_batch(q[mine], k)  # exact: escalates to the f32 scan
+                    lab, dist_, cnt = blk.views(ws["local"])
+                    sel = torch.from_numpy(mine).to(self.tdev)
+                    lab[sel] = torch.from_numpy(rl.view(np.int64)).to(self.tdev)
+                    dist_[sel] = torch.from_numpy(rd).to(self.tdev)
+                    cnt[sel] = torch.from_numpy(rc.astype(np.int32)).to(self.tdev)
+                    blk.flags(ws["local"])[sel] = 1
+                    self.last_search_escalated = int(len(mine))
+                if self.world > 1:
+                    self._exchange(ws, k)
+                    out = ws["out"]
+                else:
+                    out = ws["local"]
+                ws["h_out"].copy_(out, non_blocking=True)
+                main.synchronize()
+        labels, dists, counts = blk.views(ws["h_out"])
         return (labels.numpy().astype(np.uint64), dists.numpy().copy(), counts.numpy().astype(np.int64))

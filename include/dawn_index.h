@@ -32,8 +32,11 @@
  * sm_100 device is usable.
  *
  * Threading: the reference drives its index from a single thread
- * (src/bin/dawnsearch.rs:76-78).  Calls on one handle are serialised internally by a mutex;
- * different handles are independent.  A handle may be used from any thread.
+ * (src/bin/dawnsearch.rs:76-78); that model works unchanged.  Beyond it, search* / get are re-entrant:
+ * every host search leases its own stream + workspace (up to 8 in flight per handle), so several threads
+ * may search one handle concurrently.  add* / reserve / save / load are serialised among themselves; an
+ * add never waits for running searches (it appends beyond what they see), only a reallocation does.
+ * A handle may be used from any thread; different handles are independent.
  */
 #ifndef DAWN_INDEX_H
 #define DAWN_INDEX_H
@@ -110,6 +113,13 @@ int dawn_index_load(dawn_index *idx, const char *path);
  * search_provider.rs:183-195, served from the device corpus).  DAWN_ERR_INVALID if absent. */
 int dawn_index_get(dawn_index *idx, uint64_t label, float *vector384_out);
 
+/* SearchProvider::verify (search_provider.rs:289-327) over the device corpus: one HBM-bound pass that applies
+ * the reference's gate (finite, 0.99 < |v| < 1.01; src/search/vector.rs:185-192) to every STORED row.  The
+ * blob-length check of the reference is structural here.  Any pointer may be NULL.  The library runs the same
+ * pass incrementally over newly added rows before a search: if a stored row is longer than the gate allows,
+ * every bound of the exactness certificate is scaled accordingly (the raw ABI, like usearch, accepts any vector). */
+int dawn_index_verify(dawn_index *idx, size_t *bad_rows_out, float *min_norm_out, float *max_norm_out);
+
 /* ---- device-resident entry points (no host<->device copies inside the call) -------------
  * For callers that already hold queries / want results in device memory (a batching
  * front-end, the multi-GPU merge, bench.py's kernel-only timing).  `stream` is a
@@ -152,6 +162,10 @@ int dawn_decode_i24(const uint8_t *in1152, float *out384);
  * scan kernels as a score floor, so rows that cannot pass it are never kept, merged or re-scored. */
 int dawn_index_search_limit(dawn_index *idx, const float *query384, size_t k, float distance_limit,
                             uint64_t *labels_out, float *distances_out, size_t *count_out);
+/* The same for a batch (one limit for all queries): on the tensor-core path the limit becomes the initial
+ * threshold of every query's candidate log. */
+int dawn_index_search_batch_limit(dawn_index *idx, const float *queries, size_t batch, size_t k, float distance_limit,
+                                  uint64_t *labels_out, float *distances_out, size_t *counts_out);
 /* The peer side of a remote search: raw i24 query in (udp_service.rs:174-213). */
 int dawn_index_search_i24(dawn_index *idx, const uint8_t *query1152, size_t k, int has_limit, float distance_limit,
                           uint64_t *labels_out, float *distances_out, size_t *count_out);
@@ -176,12 +190,15 @@ int dawn_batcher_stats(dawn_batcher *b, uint64_t *batches, uint64_t *queries, ui
 const char *dawn_batcher_last_error(void);
 void dawn_batcher_free(dawn_batcher *b);
 
-/* ---- several GPUs, one process (the reference binary is one process) ---------------------------
- * One handle owns one shard per listed device.  add* places blocks of vectors round-robin on the
- * shards; search* runs every shard's exact top-k concurrently, pushes each shard's packed result
- * block over NVLink into the first device's memory (one peer copy per shard) and merges there.
- * Results are bit-identical to a single index holding everything.  (The one-process-per-GPU
- * variant with an NCCL all-gather is dawnsearch_b200/sharded.py.) */
+/* ---- several GPUs, one process (the reference binary is one process, src/bin/dawnsearch.rs:59-128) ----
+ * One handle owns one shard per listed device (NCCL communicators are created inside dawn_multi_create
+ * with ncclCommInitAll).  add* places blocks of vectors round-robin on the shards; search* runs every
+ * shard's exact top-k concurrently, exchanges the packed result blocks (k label/distance pairs per query)
+ * with ONE ncclAllGather over NVLink / NVSwitch and merges them on the first device -- the role of
+ * search_remote's scatter / gather / BestResults merge (src/search/search_service.rs:201-277).
+ * Queries a shard cannot certify are re-run exactly on that shard before the exchange, so results are
+ * bit-identical to a single index holding everything.  (The one-process-per-GPU variant under
+ * torch.distributed is dawnsearch_b200/sharded.py.) */
 typedef struct dawn_multi dawn_multi;
 int dawn_multi_create(const int *devices, size_t n_devices, uint32_t scalar, dawn_multi **out);
 void dawn_multi_free(dawn_multi *m);
@@ -197,6 +214,19 @@ size_t dawn_multi_size(const dawn_multi *m);
 size_t dawn_multi_capacity(const dawn_multi *m);
 size_t dawn_multi_shards(const dawn_multi *m);
 const char *dawn_multi_last_error(void);
+/* "exchange": 0 = auto (NCCL all-gather; peer copies when a device is listed twice or there is one shard),
+ * 1 = peer copies (cudaMemcpyPeerAsync into the first device), 2 = NCCL or fail.  Any other key is passed
+ * to every shard's dawn_index_set_option. */
+int dawn_multi_set_option(dawn_multi *m, const char *key, int64_t value);
+typedef struct dawn_multi_stats {
+    uint64_t searches, nccl_exchanges, peer_exchanges;
+    uint64_t exact_reruns;     /* (shard, query) pairs re-run exactly because a certificate failed */
+    uint64_t kernel_launches;  /* all shards */
+    double last_search_ms;     /* CUDA-event time of the slowest shard's local search in the last call */
+    double last_exchange_ms;   /* CUDA-event time of exchange + merge on the first device in the last call */
+    uint32_t nccl_ready, reserved_;
+} dawn_multi_stats;
+int dawn_multi_get_stats(dawn_multi *m, dawn_multi_stats *out);
 
 /* ---- instrumentation ------------------------------------------------------------------- */
 typedef struct dawn_profile {
@@ -210,6 +240,11 @@ typedef struct dawn_profile {
     uint64_t kernel_launches; /* all kernels launched by the library since the last reset */
     uint64_t gemm_batches;   /* batches answered by the tensor-core path (K3) */
     double gemm_ms;          /* summed CUDA-event time of those batches (all rounds, excl. finalize) */
+    /* Counted ON THE DEVICE by every finalize launch, so they also cover dawn_index_search_device (which
+     * cannot escalate: it only enqueues): results written without an exactness certificate, and the OR of
+     * every scan status word (nonzero = internal buffer overflow, a bug). */
+    uint64_t device_uncertified;
+    uint64_t device_status;
 } dawn_profile;
 /* enable != 0: record CUDA events around every K2 / finalize launch (adds host syncs when
  * read).  Off by default. */

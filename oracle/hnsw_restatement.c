@@ -87,6 +87,13 @@ typedef struct dawn_hnsw {
     heap_t cand, top, tmp;
 } dawn_hnsw;
 
+/* Scratch of one searching thread (the build uses the copy embedded in dawn_hnsw). */
+typedef struct {
+    uint32_t *visited;
+    uint32_t epoch;
+    heap_t cand, top, tmp;
+} hn_ctx;
+
 static float (*dot_fn)(const float *, const float *);
 
 static float dot_scalar(const float *a, const float *b) {
@@ -185,6 +192,33 @@ static void search_layer(dawn_hnsw *h, const float *q, uint32_t ep, float ep_d, 
                 heap_push(&h->cand, x, 0);
                 heap_push(&h->top, x, 1);
                 if (h->top.n > ef) heap_pop(&h->top, 1);
+            }
+        }
+    }
+}
+
+/* the same walk with a caller-owned scratch (read-only on the graph: safe from many threads) */
+static void search_layer_ctx(const dawn_hnsw *h, hn_ctx *c, const float *q, uint32_t ep, float ep_d, size_t ef, int l) {
+    c->epoch++;
+    c->cand.n = c->top.n = 0;
+    hn_t e = {ep_d, ep};
+    heap_push(&c->cand, e, 0);
+    heap_push(&c->top, e, 1);
+    c->visited[ep] = c->epoch;
+    while (c->cand.n) {
+        hn_t x0 = heap_pop(&c->cand, 0);
+        if (x0.d > c->top.v[0].d && c->top.n >= ef) break;
+        uint32_t *lk = links_at(h, x0.id, l);
+        for (uint32_t i = 0; i < lk[0]; i++) {
+            uint32_t nb = lk[1 + i];
+            if (c->visited[nb] == c->epoch) continue;
+            c->visited[nb] = c->epoch;
+            float d = dist(h, q, nb);
+            if (c->top.n < ef || d < c->top.v[0].d) {
+                hn_t x = {d, nb};
+                heap_push(&c->cand, x, 0);
+                heap_push(&c->top, x, 1);
+                if (c->top.n > ef) heap_pop(&c->top, 1);
             }
         }
     }
@@ -331,4 +365,87 @@ size_t dawn_hnsw_search(dawn_hnsw *h, const float *q, size_t k, uint64_t *labels
         dist_out[i] = h->tmp.v[i].d;
     }
     return n;
+}
+
+/* ---- batch entry points (no per-vector FFI overhead; several searching threads) ---------------- */
+
+int dawn_hnsw_add_batch(dawn_hnsw *h, const uint64_t *labels, const float *vecs, size_t n) {
+    for (size_t i = 0; i < n; i++)
+        if (dawn_hnsw_add(h, labels[i], vecs + i * EM)) return -1;
+    return 0;
+}
+
+static size_t search_ctx(const dawn_hnsw *h, hn_ctx *c, const float *q, size_t k, uint64_t *labels_out, float *dist_out) {
+    if (h->n == 0 || k == 0) return 0;
+    uint32_t ep = h->entry;
+    float ep_d = dist(h, q, ep);
+    for (int l = h->max_level; l > 0; l--) {
+        int changed = 1;
+        while (changed) {
+            changed = 0;
+            uint32_t *lk = links_at(h, ep, l);
+            for (uint32_t i = 0; i < lk[0]; i++) {
+                float d = dist(h, q, lk[1 + i]);
+                if (d < ep_d) {
+                    ep_d = d;
+                    ep = lk[1 + i];
+                    changed = 1;
+                }
+            }
+        }
+    }
+    size_t ef = h->efs > k ? h->efs : k;
+    search_layer_ctx(h, c, q, ep, ep_d, ef, 0);
+    size_t n = c->top.n;
+    heap_reserve(&c->tmp, n + 1);
+    memcpy(c->tmp.v, c->top.v, n * sizeof(hn_t));
+    qsort(c->tmp.v, n, sizeof(hn_t), cmp_hn);
+    if (n > k) n = k;
+    for (size_t i = 0; i < n; i++) {
+        labels_out[i] = h->label[c->tmp.v[i].id];
+        dist_out[i] = c->tmp.v[i].d;
+    }
+    return n;
+}
+
+#include <pthread.h>
+typedef struct {
+    const dawn_hnsw *h;
+    const float *q;
+    size_t nq, k, t, nt;
+    uint64_t *labels;
+    float *dist;
+    uint64_t *counts;
+} mt_job;
+
+static void *mt_worker(void *arg) {
+    mt_job *j = (mt_job *)arg;
+    hn_ctx c;
+    memset(&c, 0, sizeof c);
+    c.visited = (uint32_t *)calloc(j->h->cap ? j->h->cap : 1, sizeof(uint32_t));
+    for (size_t i = j->t; i < j->nq; i += j->nt)
+        j->counts[i] = search_ctx(j->h, &c, j->q + i * EM, j->k, j->labels + i * j->k, j->dist + i * j->k);
+    free(c.visited);
+    free(c.cand.v);
+    free(c.top.v);
+    free(c.tmp.v);
+    return NULL;
+}
+
+/* nq independent searches spread over `threads` threads (the graph is read-only while searching).
+ * threads = 1 is the reference's own model: one search thread (src/bin/dawnsearch.rs:76-78). */
+int dawn_hnsw_search_batch(const dawn_hnsw *h, const float *queries, size_t nq, size_t k, int threads, uint64_t *labels_out,
+                           float *dist_out, uint64_t *counts_out) {
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > nq) threads = (int)(nq ? nq : 1);
+    pthread_t th[256];
+    mt_job jobs[256];
+    if (threads > 256) threads = 256;
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (mt_job){h, queries, nq, k, (size_t)t, (size_t)threads, labels_out, dist_out, counts_out};
+        if (t > 0) pthread_create(&th[t], NULL, mt_worker, &jobs[t]);
+    }
+    mt_worker(&jobs[0]);
+    for (int t = 1; t < threads; t++) pthread_join(th[t], NULL);
+    return 0;
 }

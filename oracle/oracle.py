@@ -105,6 +105,11 @@ def lib() -> C.CDLL:
             L.dawn_hnsw_size.restype = C.c_size_t
             L.dawn_hnsw_size.argtypes = [C.c_void_p]
             L.dawn_hnsw_set_ef_search.argtypes = [C.c_void_p, C.c_size_t]
+            L.dawn_hnsw_add_batch.restype = C.c_int
+            L.dawn_hnsw_add_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+            L.dawn_hnsw_search_batch.restype = C.c_int
+            L.dawn_hnsw_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -331,9 +336,18 @@ class Hnsw:
 
     def add_batch(self, labels, vectors) -> None:
         vectors = _f32(vectors).reshape(-1, EM_LEN)
-        L = lib()
-        for lab, v in zip(labels, vectors):
-            L.dawn_hnsw_add(self._h, int(lab), C.c_void_p(v.ctypes.data))
+        lab = np.ascontiguousarray(labels, dtype=np.uint64)
+        assert lib().dawn_hnsw_add_batch(self._h, _p(lab), _p(vectors), vectors.shape[0]) == 0
+
+    def search_batch(self, queries, k: int, threads: int = 1):
+        """nq independent searches on `threads` threads -> (labels[nq,k], distances[nq,k], counts[nq])."""
+        q = _f32(queries).reshape(-1, EM_LEN)
+        nq = q.shape[0]
+        lo = np.zeros((nq, max(k, 1)), dtype=np.uint64)
+        do = np.zeros((nq, max(k, 1)), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint64)
+        assert lib().dawn_hnsw_search_batch(self._h, _p(q), nq, k, threads, _p(lo), _p(do), _p(cnt)) == 0
+        return lo, do, cnt.astype(np.int64)
 
     def search(self, query, k: int):
         q = _f32(query)
@@ -432,6 +446,26 @@ def make_queries(corpus_seed: int, query_seed: int, nq: int, n_rows: int,
 def planted_rows(query_seed: int, nq: int, n_rows: int, planted_fraction: float = 0.5) -> np.ndarray:
     n_pl = int(nq * planted_fraction) if n_rows > 0 else 0
     return (np_mix64(np.arange(n_pl, dtype=np.uint64) + np.uint64(query_seed + 77)) % np.uint64(max(n_rows, 1))).astype(np.int64)
+
+
+def np_clustered_rows_f32(seed: int, first_row: int, n: int, centers: int = 1024, intrinsic: int = 24,
+                          spread: float = 0.8, iso: float = 0.15) -> np.ndarray:
+    """A corpus shaped more like sentence embeddings than i.i.d. noise: a mixture of `centers` unit centres;
+    a row = normalize(centre + spread * (low-dimensional offset in a shared `intrinsic`-dim subspace) +
+    iso * isotropic noise).  Same-cluster rows have cosine ~ 1/(1+spread^2+iso^2) ~ 0.6, the neighbourhood of
+    a row has intrinsic dimension ~`intrinsic` instead of 384.  Row r depends only on (seed, r), so shards
+    and chunks agree.  Used for the recall report of the HNSW stand-in (graph indexes are at their worst on
+    isotropic noise); NOT a claim about MiniLM's actual distribution."""
+    cen = np_synth_rows_f32(seed ^ 0xC3A5C85C, 0, centers).astype(np.float64)                # unit centres
+    basis = np_synth_rows_f32(seed ^ 0x5BD1E995, 0, intrinsic).astype(np.float64)            # subspace rows (~orthogonal)
+    rows = np.arange(n, dtype=np.uint64) + np.uint64(first_row)
+    which = (np_mix64(rows + np.uint64(seed + 1234567)) % np.uint64(centers)).astype(np.int64)
+    g_iso = np_synth_rows_f32(seed ^ 0x27D4EB2F, first_row, n).astype(np.float64)            # unit, isotropic
+    z = np_synth_rows_f32(seed ^ 0x165667B1, first_row, n).astype(np.float64)[:, :intrinsic]  # ~N(0, 1/384) coords
+    z *= np.sqrt(EM_LEN / intrinsic)                                                          # |z| ~ 1
+    x = cen[which] + spread * (z @ basis) + iso * g_iso
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return x.astype(np.float32)
 
 
 def np_store_i8(rows: np.ndarray):

@@ -33,10 +33,23 @@ extern "C" {
     fn dawn_batcher_create(idx: *mut c_void, max_batch: usize, max_wait_us: u32, out: *mut *mut c_void) -> c_int;
     fn dawn_batcher_search(b: *mut c_void, q: *const f32, k: usize, labels: *mut u64, dist: *mut f32, count: *mut usize) -> c_int;
     fn dawn_batcher_free(b: *mut c_void);
+    fn dawn_index_verify(idx: *mut c_void, bad_rows: *mut usize, min_norm: *mut f32, max_norm: *mut f32) -> c_int;
+    // several GPUs, one process: shards + one NCCL all-gather + device merge inside the library
+    fn dawn_multi_create(devices: *const c_int, n_devices: usize, scalar: u32, out: *mut *mut c_void) -> c_int;
+    fn dawn_multi_free(m: *mut c_void);
+    fn dawn_multi_reserve(m: *mut c_void, n_total: usize) -> c_int;
+    fn dawn_multi_add(m: *mut c_void, label: u64, v: *const f32) -> c_int;
+    fn dawn_multi_add_batch(m: *mut c_void, labels: *const u64, v: *const f32, n: usize) -> c_int;
+    fn dawn_multi_search(m: *mut c_void, q: *const f32, k: usize, labels: *mut u64, dist: *mut f32, count: *mut usize) -> c_int;
+    fn dawn_multi_search_batch(m: *mut c_void, q: *const f32, batch: usize, k: usize, labels: *mut u64, dist: *mut f32, counts: *mut usize) -> c_int;
+    fn dawn_multi_size(m: *const c_void) -> usize;
+    fn dawn_multi_capacity(m: *const c_void) -> usize;
+    fn dawn_multi_shards(m: *const c_void) -> usize;
+    fn dawn_multi_last_error() -> *const c_char;
 }
 
 #[derive(Clone, Copy)] pub enum MetricKind { IP }
-#[derive(Clone, Copy)] pub enum ScalarKind { F32, F16, F8 }   // F32 is accepted and stored as F16 on the device
+#[derive(Clone, Copy)] pub enum ScalarKind { F32, F16, F8 }
 
 pub struct IndexOptions {          // same fields as usearch::ffi::IndexOptions (search_provider.rs:35-42)
     pub dimensions: usize, pub metric: MetricKind, pub quantization: ScalarKind,
@@ -46,16 +59,25 @@ pub struct IndexOptions {          // same fields as usearch::ffi::IndexOptions 
 pub struct Matches { pub labels: Vec<u64>, pub distances: Vec<f32> }   // search_provider.rs:221
 
 pub struct Index { h: *mut c_void }
-unsafe impl Send for Index {}      // the library serialises calls on a handle internally
+unsafe impl Send for Index {}      // a handle may be used from any thread
+unsafe impl Sync for Index {}      // search* / get are re-entrant, add* / reserve / save / load are serialised inside the library
 
 fn err() -> anyhow::Error {
     anyhow::anyhow!(unsafe { CStr::from_ptr(dawn_last_error()) }.to_string_lossy().into_owned())
 }
 fn ck(rc: c_int) -> anyhow::Result<()> { if rc == 0 { Ok(()) } else { Err(err()) } }
 
+// usearch ScalarKind -> DAWN_SCALAR_*: F32 keeps the original f32 rows beside the fp16 selection copy, so distances are
+// those of an exact f32 brute force over the vectors as given (what the reference's ScalarKind::F32 index stores,
+// search_provider.rs:38); F16 = fp16 rows only (768 B / page); F8 = int8 + per-vector scale (388 B / page).
+fn scalar_code(q: ScalarKind) -> u32 { match q { ScalarKind::F16 => 0, ScalarKind::F8 => 1, ScalarKind::F32 => 2 } }
+
 pub fn new_index(o: &IndexOptions) -> anyhow::Result<Box<Index>> {       // search_provider.rs:102
-    let scalar = match o.quantization { ScalarKind::F8 => 1, _ => 0 };   // F8 -> int8 storage (388 B / page), F32/F16 -> fp16
-    let opts = DawnOptions { dimensions: o.dimensions as u32, metric: 0, scalar, device: 0, capacity: 0, flags: 0, reserved: 0 };
+    new_index_on(o, 0)
+}
+/// `new_index` on a chosen CUDA device (the reference has no such knob: USearch runs on the CPU).
+pub fn new_index_on(o: &IndexOptions, device: i32) -> anyhow::Result<Box<Index>> {
+    let opts = DawnOptions { dimensions: o.dimensions as u32, metric: 0, scalar: scalar_code(o.quantization), device, capacity: 0, flags: 0, reserved: 0 };
     let mut h = std::ptr::null_mut();
     ck(unsafe { dawn_index_create(&opts, &mut h) })?;
     Ok(Box::new(Index { h }))
@@ -124,7 +146,61 @@ impl Index {
     pub fn view(&self, path: &str) -> anyhow::Result<()> { self.load(path) }          // examples_old/search_usearch.rs:47
 }
 
+impl Index {
+    /// `SearchProvider::verify` (search_provider.rs:289-327) over the device corpus: (rows failing the norm gate, min |v|, max |v|).
+    pub fn verify(&self) -> anyhow::Result<(usize, f32, f32)> {
+        let (mut bad, mut lo, mut hi) = (0usize, 0f32, 0f32);
+        ck(unsafe { dawn_index_verify(self.h, &mut bad, &mut lo, &mut hi) })?;
+        Ok((bad, lo, hi))
+    }
+}
+
 impl Drop for Index { fn drop(&mut self) { unsafe { dawn_index_free(self.h) } } }
+
+/// The corpus sharded over several B200s of one box, owned by THIS process (the reference binary is one process,
+/// src/bin/dawnsearch.rs:59-128).  Same method names as `Index`, so `SearchProvider` can hold either.  Every search is:
+/// local exact top-k on each GPU -> one NCCL all-gather of k (label, distance) pairs per query -> device merge; the
+/// on-box analogue of `search_remote` (src/search/search_service.rs:201-277).
+pub struct MultiIndex { m: *mut c_void }
+unsafe impl Send for MultiIndex {}
+fn merr() -> anyhow::Error {
+    anyhow::anyhow!(unsafe { CStr::from_ptr(dawn_multi_last_error()) }.to_string_lossy().into_owned())
+}
+fn mck(rc: c_int) -> anyhow::Result<()> { if rc == 0 { Ok(()) } else { Err(merr()) } }
+impl MultiIndex {
+    pub fn new(devices: &[i32], quantization: ScalarKind) -> anyhow::Result<MultiIndex> {
+        let mut m = std::ptr::null_mut();
+        mck(unsafe { dawn_multi_create(devices.as_ptr(), devices.len(), scalar_code(quantization), &mut m) })?;
+        Ok(MultiIndex { m })
+    }
+    pub fn reserve(&self, capacity: usize) -> anyhow::Result<()> { mck(unsafe { dawn_multi_reserve(self.m, capacity) }) }
+    pub fn add(&self, label: u64, vector: &[f32]) -> anyhow::Result<()> {
+        anyhow::ensure!(vector.len() == 384, "vector must have 384 dimensions");
+        mck(unsafe { dawn_multi_add(self.m, label, vector.as_ptr()) })
+    }
+    pub fn add_batch(&self, labels: &[u64], vectors: &[f32]) -> anyhow::Result<()> {
+        anyhow::ensure!(vectors.len() == labels.len() * 384, "vectors must be labels.len() x 384");
+        mck(unsafe { dawn_multi_add_batch(self.m, labels.as_ptr(), vectors.as_ptr(), labels.len()) })
+    }
+    pub fn search(&self, query: &[f32], count: usize) -> anyhow::Result<Matches> {
+        anyhow::ensure!(query.len() == 384, "query must have 384 dimensions");
+        let (mut labels, mut distances, mut n) = (vec![0u64; count], vec![0f32; count], 0usize);
+        mck(unsafe { dawn_multi_search(self.m, query.as_ptr(), count, labels.as_mut_ptr(), distances.as_mut_ptr(), &mut n) })?;
+        labels.truncate(n); distances.truncate(n);
+        Ok(Matches { labels, distances })
+    }
+    pub fn search_batch(&self, queries: &[f32], count: usize) -> anyhow::Result<Vec<Matches>> {
+        let b = queries.len() / 384;
+        let (mut labels, mut distances, mut counts) = (vec![0u64; b * count], vec![0f32; b * count], vec![0usize; b]);
+        mck(unsafe { dawn_multi_search_batch(self.m, queries.as_ptr(), b, count, labels.as_mut_ptr(), distances.as_mut_ptr(), counts.as_mut_ptr()) })?;
+        Ok((0..b).map(|i| Matches { labels: labels[i * count..i * count + counts[i]].to_vec(),
+                                    distances: distances[i * count..i * count + counts[i]].to_vec() }).collect())
+    }
+    pub fn size(&self) -> usize { unsafe { dawn_multi_size(self.m) } }
+    pub fn capacity(&self) -> usize { unsafe { dawn_multi_capacity(self.m) } }
+    pub fn shards(&self) -> usize { unsafe { dawn_multi_shards(self.m) } }
+}
+impl Drop for MultiIndex { fn drop(&mut self) { unsafe { dawn_multi_free(self.m) } } }
 
 /// Micro-batching front for `SearchService` (src/search/search_service.rs:55-104): any number of threads call
 /// `search` with one query each; a worker thread inside the library answers them in batches, which is what feeds the
