@@ -57,7 +57,7 @@ constexpr float kGemmAccumSlack = 6.0e-5f;  // K3: tensor-core f32 accumulation 
 constexpr float kRowNormGate = 1.0105f;     // the reference's gate (vector.rs:185-192) plus fp16 / int8 rounding
 constexpr int kMaxPoolWs = 8;               // host searches in flight per handle
 constexpr size_t kBulkMinRows = 32768;      // add_batch calls at least this large take the parallel bulk pipeline
-constexpr int kBulkThreads = 4;
+constexpr int kBulkThreads = 12;       // copier threads (lanes) of the bulk-load pipeline; DAWN_BULK_THREADS uses fewer
 
 // merge kernel for sharded searches, defined at the bottom of this file
 cudaError_t launch_merge_results(const uint64_t *labels, const float *dist, const uint32_t *counts,
@@ -174,7 +174,7 @@ struct dawn_index {
     // int8 corpora: batches of at least this many queries take the tensor cores.  0 = never.
     std::atomic<int64_t> i8_tensor_min_batch{16};
     std::atomic<int64_t> i8_tensor_chunk_rows{4 << 20};
-    std::atomic<int64_t> i8_native{1};  // 1 = tcgen05 kind::i8 straight from the int8 arena, 0 = dequantise to fp16 tiles
+    std::atomic<int64_t> i8_native{0};  // 1 = tcgen05 kind::i8 straight from the int8 arena, 0 = dequantise to fp16 tiles
 
     // search workspaces
     std::mutex pool_mu;
@@ -1020,12 +1020,17 @@ int bulk_add(dawn_index *idx, const uint64_t *labels, const float *vectors, size
     if (rc) return rc;
     const size_t at = idx->size;
     const size_t n_slices = (n + kStageRowsHost - 1) / kStageRowsHost;
+    static const int lanes = [] {
+        const char *e = getenv("DAWN_BULK_THREADS");
+        int v = e ? atoi(e) : 8;
+        return v < 1 ? 1 : (v > kBulkThreads ? kBulkThreads : v);
+    }();
     std::atomic<int> err{0};
     auto lane_fn = [&](int t) {
         cudaSetDevice(idx->device);
         BulkLane &L = idx->bulk[t];
         int turn = 0;
-        for (size_t sl = (size_t)t; sl < n_slices && !err; sl += kBulkThreads, turn ^= 1) {
+        for (size_t sl = (size_t)t; sl < n_slices && !err; sl += lanes, turn ^= 1) {
             const size_t r0 = sl * kStageRowsHost;
             const size_t cnt = n - r0 < kStageRowsHost ? n - r0 : kStageRowsHost;
             if (L.busy[turn]) {
@@ -1048,9 +1053,9 @@ int bulk_add(dawn_index *idx, const uint64_t *labels, const float *vectors, size
         L.busy[0] = L.busy[1] = false;
     };
     std::thread th[kBulkThreads];
-    for (int t = 1; t < kBulkThreads; t++) th[t] = std::thread(lane_fn, t);
+    for (int t = 1; t < lanes; t++) th[t] = std::thread(lane_fn, t);
     lane_fn(0);
-    for (int t = 1; t < kBulkThreads; t++) th[t].join();
+    for (int t = 1; t < lanes; t++) th[t].join();
     if (err) {
         idx->dead = true;
         cudaError_t e = cudaGetLastError();
