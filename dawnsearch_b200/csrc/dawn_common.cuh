@@ -204,4 +204,28 @@ struct GemmSearch {
 cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s);
 size_t gemm_workspace_bytes(int n_queries);
 
+
+// K4c: tcgen05 kind::i8 GEMM + fused filter straight from the blocked int8 arena, exact re-score between rounds (gemm_i8.cu).
+struct GemmSearchI8 {
+    const uint8_t *arena;     // blocked int8 arena (8 rows + 8 f32 scales per 3104-byte block)
+    const uint64_t *labels;   // [n_rows]
+    uint64_t n_rows;
+    const float *queries;     // [n_queries][384] f32, device
+    int n_queries;
+    int kprime;               // candidates kept per query (<= 128); exact scores, so k' >= k is all it takes
+    int grid;                 // CTAs (= SM count)
+    int cta_group;            // 0 = auto (pairs when more than 128 queries), 1 or 2 to force
+    int chunk_tiles;          // 0 = auto
+    int sequential_tiles;     // 1 = visit tiles in stored order (A/B only)
+    int growth;               // 0 = automatic
+    void *workspace;          // gemm_i8_workspace_bytes(n_queries)
+    Cand *final_lists;        // out: [ceil256(n_queries)][kprime] candidates with EXACT scores (unsorted)
+    float limit_score;        // 1 - distance_limit (-inf = none)
+    float eps_scale;          // > 1 when stored rows are longer than the reference's norm gate allows
+    const uint32_t **overflow_out;  // out: device pointer to per-query overflow flags
+    int *launches_out;        // out: kernels launched
+};
+cudaError_t launch_gemm_search_i8(const GemmSearchI8 &p, cudaStream_t s);
+size_t gemm_i8_workspace_bytes(int n_queries);
+
 }  // namespace dawn

@@ -174,7 +174,7 @@ struct dawn_index {
     // int8 corpora: batches of at least this many queries take the tensor cores.  0 = never.
     std::atomic<int64_t> i8_tensor_min_batch{16};
     std::atomic<int64_t> i8_tensor_chunk_rows{4 << 20};
-    std::atomic<int64_t> i8_native{0};  // 1 = tcgen05 kind::i8 straight from the int8 arena, 0 = dequantise to fp16 tiles
+    std::atomic<int64_t> i8_native{1};  // 1 = tcgen05 kind::i8 straight from the int8 arena, 0 = dequantise to fp16 tiles
 
     // search workspaces
     std::mutex pool_mu;
@@ -704,6 +704,64 @@ int search_i8_tensor(dawn_index *idx, SearchWs *ws, const float *d_queries, size
     return run_finalize(idx, ws, fl, s, batch);
 }
 
+// int8 corpus, large batch, native variant (gemm_i8.cu): tcgen05 kind::i8 straight from the int8 arena; the rounds leave
+// the k' best rows by EXACT score, finalize orders them.
+int search_i8_native(dawn_index *idx, SearchWs *ws, const float *d_queries, size_t batch, size_t k, int kprime,
+                     uint64_t *d_labels_out, float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags, cudaStream_t s,
+                     uint32_t *d_status_out) {
+    const size_t qp = (batch + 255) / 256 * 256;
+    int rc;
+    if ((rc = ensure_gemm_ws(idx, ws, gemm_i8_workspace_bytes((int)batch)))) return rc;
+    if ((rc = ensure_dev(idx, &ws->d_partials, &ws->partials_cap, qp * kprime))) return rc;
+    if ((rc = prepare_counters(idx, ws, 1, s))) return rc;
+    GemmSearchI8 gs{};
+    gs.arena = arena_i8(idx);
+    gs.labels = idx->labels;
+    gs.n_rows = ws->n_rows;
+    gs.queries = d_queries;
+    gs.n_queries = (int)batch;
+    gs.kprime = kprime;
+    gs.grid = idx->sm_count;
+    gs.cta_group = (int)idx->gemm_cta_group;
+    gs.chunk_tiles = (int)idx->gemm_chunk_tiles;
+    gs.sequential_tiles = (int)idx->gemm_sequential_tiles;
+    gs.growth = (int)idx->gemm_growth;
+    gs.workspace = ws->d_gemm_ws;
+    gs.final_lists = ws->d_partials;
+    gs.limit_score = ws->eps_scale == 1.0f ? ws->limit_score : -INFINITY;
+    gs.eps_scale = ws->eps_scale;
+    const uint32_t *overflow = nullptr;
+    int launches = 0;
+    gs.overflow_out = &overflow;
+    gs.launches_out = &launches;
+    EventPair evg;
+    bool timedg = begin_event(idx, ws, 2, s, &evg);
+    CK(idx, launch_gemm_search_i8(gs, s));
+    if (timedg) end_event(ws, evg, s);
+    ws->prof.gemm_batches++;
+    ws->prof.kernel_launches += launches;
+    FinalizeLaunch fl{};
+    fl.corpus = idx->corpus;
+    fl.queries = d_queries;
+    fl.nq = (int)batch;
+    fl.partials = ws->d_partials;
+    fl.n_lists = 1;
+    fl.kprime = kprime;
+    fl.k = (int)k;
+    fl.eps = 0.f;  // the candidates carry exact scores: a row outside the list scores strictly below its weakest member
+    fl.labels_out = d_labels_out;
+    fl.distances_out = d_dist_out;
+    fl.counts_out = d_counts;
+    fl.flags_out = d_flags;
+    fl.scalar = 1;
+    fl.eps_q = nullptr;
+    fl.overflow = overflow;
+    fl.counters = ws->d_counters;
+    fl.n_counters = 1;
+    fl.status_out = d_status_out;
+    return run_finalize(idx, ws, fl, s, batch);
+}
+
 // Enqueue the whole search for `batch` device-resident queries on stream `s`.  The caller holds the shared
 // corpus lock; ws->n_rows / eps_scale / limit_score describe the snapshot being searched.
 int search_enqueue(dawn_index *idx, SearchWs *ws, const float *d_queries, size_t batch, size_t k, int kprime,
@@ -715,7 +773,10 @@ int search_enqueue(dawn_index *idx, SearchWs *ws, const float *d_queries, size_t
     // a pushed-down limit is only sound with the nominal eps values
     const float limit_score = ws->eps_scale == 1.0f ? ws->limit_score : -INFINITY;
     if (idx->scalar == DAWN_SCALAR_I8 && !scan_only && idx->i8_tensor_min_batch > 0 &&
-        (int64_t)batch >= idx->i8_tensor_min_batch && n >= 65536 && k <= 100 && !idx->i8_native)
+        (int64_t)batch >= idx->i8_tensor_min_batch && n >= 65536 && idx->i8_native)
+        return search_i8_native(idx, ws, d_queries, batch, k, kprime, d_labels_out, d_dist_out, d_counts, d_flags, s, d_status_out);
+    if (idx->scalar == DAWN_SCALAR_I8 && !scan_only && idx->i8_tensor_min_batch > 0 &&
+        (int64_t)batch >= idx->i8_tensor_min_batch && n >= 65536 && k <= 100)
         return search_i8_tensor(idx, ws, d_queries, batch, k, kprime, d_labels_out, d_dist_out, d_counts, d_flags, s, d_status_out);
     if (idx->scalar == DAWN_SCALAR_I8) {
         // K4: int8 storage -> streaming dp4a scan, 1 or 2 queries per pass, exact f32 re-score

@@ -1,0 +1,665 @@
+// gemm_i8.cu -- K4c: large batches over an int8-stored corpus on the INT8 tensor cores
+// (tcgen05.mma kind::i8, s32 accumulators in TMEM), straight from the blocked int8 arena: no dequantisation pass,
+// no scratch.  Replaces usearch's Index::search (/root/reference/src/search/search_provider.rs:214) for batches over
+// ScalarKind::F8-style storage (precedent: examples_old/search_usearch.rs:38, distance_i8 at src/search/vector.rs:157-163).
+//
+// Roofline: int8 tensor pipe for batch >~ 256 (2*B*N*384 int8 op), HBM below (388 B per row per pass).
+//
+// How exactness survives an 8-bit query.  The MMA computes HI = sum_i hi_i * x8_i with ONE int8 level of the query
+// (q ~ s1 * hi, |q - s1 hi|_2 =: delta ~ 8e-3), i.e. an approximate score a = s1 * s_row * HI with
+// |a - exact| <= e1 = 1.03 * delta + 3e-6 (Cauchy-Schwarz; dequantised rows have norm < 1.02; the integer dot product
+// itself is exact).  That is too loose to certify a top-k from approximate scores, so approximate scores are never
+// ranked.  Instead:
+//   * the epilogue only FILTERS: a row is appended to the query's candidate log iff a >= thr;
+//   * select_i8_kernel re-scores every NEW log entry EXACTLY (the oracle's sequential f32 sum over the int8 row, times
+//     the row scale: oracle/dawn_oracle.c:dawn_oracle_search_i8), keeps the best k' by exact score and publishes
+//     thr = (k'-th best EXACT score) - e1 for the next round.
+// A row the filter drops has a < T - e1, hence exact < T, hence it is not among the k' best: after the last round the
+// log holds exactly the k' best rows of the whole corpus by exact score, whatever the distribution of the data.  The
+// price of the one-level query is only a wider filter band (~2x more survivors on the synthetic corpus), not slack in
+// the answer.  finalize.cu then orders them and emits 1 - score; its certificate sees exact scores (eps = 0).
+// A log overflow (more than 2048 survivors in a round: massive near-ties) flags the query; the host API re-runs it
+// through the exact scan, as on the fp16 path.
+//
+// Shape of one CTA (384 threads, 1 CTA/SM, persistent over work units):
+//   A operand  = one 128-query tile of hi (int8), K-major, resident in shared memory: 3 k-blocks of 128 rows x 128 B  48 KB
+//   B operand  = corpus tiles of 256 rows = 32 arena blocks, streamed k-block by k-block (256 x 128 B = 32 KB per stage)
+//                by a 3-D TMA tensor map over the blocked arena {384 B row, 8 rows per block, blocks of 3104 B}    96 KB ring
+//   scales     = the tile's 256 per-row f32 scales (they sit behind each block's rows), their own 2-D TMA map      8 x 1 KB ring
+//   D          = 128 x 256 s32 in TMEM, two buffers; 12 MMAs (K = 32) per tile
+//   warp 0 TMA producer, warp 1 MMA issuer + TMEM alloc, warps 4-11 epilogue: two warps per TMEM lane quarter, each
+//   taking half of the tile's columns: tcgen05.ld -> I2F -> * scale -> max tree -> compare with the query's threshold.
+//   CTA pairs (cta_group::2, M = 256) as in gemm_topk.cu when there is more than one query tile.
+#include <cuda.h>
+
+#include <cmath>
+
+#include "dawn_common.cuh"
+#include "gemm_pipe.cuh"
+
+namespace dawn {
+
+namespace {
+
+using namespace pipe;
+
+constexpr int kI8Threads = 384;
+constexpr int BM = 128;             // queries per tile (UMMA M)
+constexpr int BN = 256;             // corpus rows per tile (UMMA N) = 32 arena blocks
+constexpr int BKB = 128;            // int8 elements (= bytes) per k-block = one swizzle-atom row
+constexpr int kKBlocks = kDim / BKB;  // 3
+constexpr int kUmmaKBytes = 32;     // one kind::i8 MMA covers K = 32
+constexpr int kMaxStagesB = 6;      // 3 x 32 KB (one CTA) or 6 x 16 KB (CTA pair)
+constexpr int kBRingBytes = 3 * BN * BKB;      // 98304 either way
+constexpr int kABlockBytes = BM * BKB;         // 16384
+constexpr int kABytes = kABlockBytes * kKBlocks;  // 49152
+constexpr int kTmemCols = 512;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kStageCap = 16;       // survivors an epilogue thread parks in shared memory before one atomic flush
+constexpr int kStagingBytes = kStageCap * kEpiThreads * 8;  // 32 KB
+constexpr int kScaleSlots = 8;      // scale tiles in flight; the producer runs at most 4 tiles ahead of the epilogue
+constexpr int kScaleTileBytes = BN * 4;
+constexpr int kBarBytes = 512;
+constexpr int kSmemBytes = 1024 + kABytes + kBRingBytes + kBarBytes + kScaleSlots * kScaleTileBytes + kStagingBytes;
+
+// Instruction descriptor for kind::i8: D = s32 (c_format 2 at bit 4), A = B = signed int8 (format 1 at bits 7 and 10),
+// both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc_i8(int m) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct I8Smem {  // offsets from the 1024-aligned base
+    static constexpr int a_off = 0;
+    static constexpr int b_off = kABytes;
+    static constexpr int bar_off = kABytes + kBRingBytes;
+    static constexpr int scale_off = bar_off + kBarBytes;
+    static constexpr int staging_off = scale_off + kScaleSlots * kScaleTileBytes;
+    // barriers (8 B each): full[6], empty[6], tmem_full[2], tmem_empty[2], a_full, a_free, scale_full[8]; then tmem ptr
+};
+
+__device__ __noinline__ void flush_staged_i8(uint32_t stage_smem, int col, uint32_t n, uint2 *__restrict__ log_q,
+                                             uint32_t *__restrict__ cnt_q, uint32_t *__restrict__ overflow_q, int cap) {
+    uint32_t slot = atomicAdd(cnt_q, n);
+    for (uint32_t e = 0; e < n; e++, slot++) {
+        uint2 val;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(val.x), "=r"(val.y) : "r"(stage_smem + (e * kEpiThreads + col) * 8));
+        if (slot < (uint32_t)cap) log_q[slot] = val;
+        else *overflow_q = 1u;
+    }
+}
+
+template <int CG>
+__global__ void __launch_bounds__(kI8Threads, 1)
+gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+                    const __grid_constant__ CUtensorMap tmap_s, uint32_t tile_begin, uint32_t tile_end, uint32_t n_rows,
+                    uint32_t n_tiles_total, uint32_t perm_mult, int n_qtiles, int n_queries, int chunk_tiles,
+                    const float *__restrict__ thr_g, uint32_t *__restrict__ cnt_g, uint2 *__restrict__ log_g,
+                    uint32_t *__restrict__ overflow_g, int log_cap) {
+    constexpr int kStagesB = 3 * CG;
+    constexpr int kBRows = BN / CG;                  // corpus rows this CTA streams per tile
+    constexpr int kBStageBytes = kBRows * BKB;       // 32 KB or 16 KB
+    constexpr uint32_t kIdesc = make_idesc_i8(BM * CG);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_smem = base + I8Smem::a_off;
+    const uint32_t b_smem = base + I8Smem::b_off;
+    const uint32_t bars = base + I8Smem::bar_off;
+    const uint32_t scale_smem = base + I8Smem::scale_off;
+    auto full_bar = [&](int s) { return bars + 8 * s; };
+    auto empty_bar = [&](int s) { return bars + 8 * (kMaxStagesB + s); };
+    auto tfull_bar = [&](int a) { return bars + 8 * (2 * kMaxStagesB + a); };
+    auto tempty_bar = [&](int a) { return bars + 8 * (2 * kMaxStagesB + 2 + a); };
+    const uint32_t a_full_bar = bars + 8 * (2 * kMaxStagesB + 4);
+    const uint32_t a_free_bar = bars + 8 * (2 * kMaxStagesB + 5);
+    auto sfull_bar = [&](int s) { return bars + 8 * (2 * kMaxStagesB + 6 + s); };
+    const uint32_t tmem_ptr_smem = bars + 8 * (2 * kMaxStagesB + 6 + kScaleSlots);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+    const uint32_t unit_first = blockIdx.x / CG;
+    const uint32_t unit_stride = gridDim.x / CG;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStagesB; s++) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), kEpiWarps * CG);  // one arrival per epilogue warp (of both CTAs)
+        }
+        mbar_init(a_full_bar, 1);
+        mbar_init(a_free_bar, 1);
+        for (int s = 0; s < kScaleSlots; s++) mbar_init(sfull_bar(s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        if constexpr (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_smem),
+                         "r"((uint32_t)kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_smem),
+                         "r"((uint32_t)kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+    }
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all();
+    else __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+    // Work units and the strided visiting permutation: as in gemm_topk.cu.
+    const uint32_t n_tiles = tile_end - tile_begin;
+    auto phys_row0 = [&](uint32_t tile) {
+        return (uint32_t)(((uint64_t)(tile_begin + tile) * perm_mult) % n_tiles_total) * (uint32_t)BN;
+    };
+    const uint32_t n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
+    const uint32_t n_units = n_chunks * (uint32_t)n_qtiles;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer (both CTAs of a pair) =====================
+        uint32_t g = 0, n_reload = 0, tile_ctr = 0;
+        int cur_t = -1;
+        for (uint32_t u = unit_first; u < n_units; u += unit_stride) {
+            const int t = (int)(u % (uint32_t)n_qtiles);
+            const uint32_t chunk = u / (uint32_t)n_qtiles;
+            if (t != cur_t) {
+                if (n_reload > 0) mbar_wait(a_free_bar, (n_reload - 1) & 1u);
+                const int qrow = t * BM * CG + (int)cta_rank * BM;
+                if constexpr (CG == 2) {
+                    if (cta_rank == 0) mbar_expect_tx(a_full_bar, 2 * kABytes);
+                    const uint32_t lead = mapa_rank(a_full_bar, 0);
+                    for (int kb = 0; kb < kKBlocks; kb++)
+                        tma_load_2d_pair(a_smem + kb * kABlockBytes, &tmap_q, kb * BKB, qrow, lead);
+                } else {
+                    mbar_expect_tx(a_full_bar, kABytes);
+                    for (int kb = 0; kb < kKBlocks; kb++)
+                        tma_load_2d(a_smem + kb * kABlockBytes, &tmap_q, kb * BKB, qrow, a_full_bar);
+                }
+                cur_t = t;
+                n_reload++;
+            }
+            const uint32_t tile0 = chunk * chunk_tiles;
+            const uint32_t tile1 = min(n_tiles, tile0 + chunk_tiles);
+            for (uint32_t tile = tile0; tile < tile1; tile++, tile_ctr++) {
+                const uint32_t prow0 = phys_row0(tile);
+                // The whole tile's 256 scales for THIS CTA's epilogue (each CTA of a pair filters all 256 columns
+                // for its own 128 queries).  The slot being overwritten belonged to the tile 8 back; the B ring and
+                // the two accumulators keep this producer at most 4 tiles ahead of the epilogue, so it is free.
+                {
+                    const uint32_t sl = tile_ctr % kScaleSlots;
+                    mbar_expect_tx(sfull_bar(sl), kScaleTileBytes);
+                    tma_load_2d(scale_smem + sl * kScaleTileBytes, &tmap_s, 0, (int)(prow0 / kI8BlockRows), sfull_bar(sl));
+                }
+                const int blk0 = (int)((prow0 + cta_rank * kBRows) / kI8BlockRows);
+                for (int kb = 0; kb < kKBlocks; kb++, g++) {
+                    const uint32_t s = g % kStagesB;
+                    mbar_wait(empty_bar(s), ((g / kStagesB) & 1u) ^ 1u);
+                    if constexpr (CG == 2) {
+                        if (cta_rank == 0) mbar_expect_tx(full_bar(s), 2 * kBStageBytes);
+                        tma_load_3d_pair(b_smem + s * kBStageBytes, &tmap_x, kb * BKB, 0, blk0, mapa_rank(full_bar(s), 0));
+                    } else {
+                        mbar_expect_tx(full_bar(s), kBStageBytes);
+                        tma_load_3d(b_smem + s * kBStageBytes, &tmap_x, kb * BKB, 0, blk0, full_bar(s));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        uint32_t g = 0, tile_ctr = 0, a_loads = 0;
+        int cur_t = -1;
+        for (uint32_t u = unit_first; u < n_units; u += unit_stride) {
+            const int t = (int)(u % (uint32_t)n_qtiles);
+            const uint32_t chunk = u / (uint32_t)n_qtiles;
+            if (t != cur_t) {
+                mbar_wait(a_full_bar, a_loads & 1u);
+                a_loads++;
+                cur_t = t;
+            }
+            const uint32_t tile0 = chunk * chunk_tiles;
+            const uint32_t tile1 = min(n_tiles, tile0 + chunk_tiles);
+            for (uint32_t tile = tile0; tile < tile1; tile++, tile_ctr++) {
+                const uint32_t acc = tile_ctr & 1u;
+                mbar_wait(tempty_bar(acc), ((tile_ctr >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < kKBlocks; kb++, g++) {
+                    const uint32_t s = g % kStagesB;
+                    mbar_wait(full_bar(s), (g / kStagesB) & 1u);
+                    tc_fence_after();
+                    const uint64_t adesc = make_kmajor_sw128_desc(a_smem + kb * kABlockBytes);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(b_smem + s * kBStageBytes);
+#pragma unroll
+                    for (int k = 0; k < BKB / kUmmaKBytes; k++) {
+                        // advance 32 bytes inside the swizzle atom: +2 in 16-byte units
+                        if constexpr (CG == 2)
+                            tc_mma_i8_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
+                                           (uint32_t)((kb | k) != 0));
+                        else
+                            tc_mma_i8(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
+                                      (uint32_t)((kb | k) != 0));
+                    }
+                    if constexpr (CG == 2) tc_commit_pair(empty_bar(s));
+                    else tc_commit(empty_bar(s));
+                }
+                if constexpr (CG == 2) tc_commit_pair(tfull_bar(acc));
+                else tc_commit(tfull_bar(acc));
+            }
+            const uint32_t u_next = u + unit_stride;
+            if (u_next < n_units && (int)(u_next % (uint32_t)n_qtiles) != t) {
+                if constexpr (CG == 2) tc_commit_pair(a_free_bar);
+                else tc_commit(a_free_bar);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: scale, threshold filter =====================
+        const int quarter = warp & 3;          // TMEM lane quarter this warp may read
+        const int half = (warp - 4) >> 2;      // which 128 of the tile's 256 columns this warp filters
+        const int col = (warp - 4) * 32 + lane;  // this thread's column in the staging area
+        const uint32_t stage_smem = base + I8Smem::staging_off;
+        uint32_t n_st = 0;
+        uint32_t tile_ctr = 0;
+        const uint32_t tempty_lead0 = CG == 2 ? mapa_rank(tempty_bar(0), 0) : 0u;
+        const uint32_t tempty_lead1 = CG == 2 ? mapa_rank(tempty_bar(1), 0) : 0u;
+        for (uint32_t u = unit_first; u < n_units; u += unit_stride) {
+            const int t = (int)(u % (uint32_t)n_qtiles);
+            const uint32_t chunk = u / (uint32_t)n_qtiles;
+            const int q = t * BM * CG + (int)cta_rank * BM + quarter * 32 + lane;
+            const bool q_valid = q < n_queries;
+            const float thr = q_valid ? thr_g[q] : __int_as_float(0x7f800000);  // in units of s_row * HI
+            uint2 *log_q = log_g + (size_t)q * log_cap;
+            const uint32_t tile0 = chunk * chunk_tiles;
+            const uint32_t tile1 = min(n_tiles, tile0 + chunk_tiles);
+            for (uint32_t tile = tile0; tile < tile1; tile++, tile_ctr++) {
+                const uint32_t acc = tile_ctr & 1u;
+                const uint32_t row0 = phys_row0(tile);
+                const uint32_t sl = tile_ctr % kScaleSlots;
+                mbar_wait(sfull_bar(sl), (tile_ctr / kScaleSlots) & 1u);
+                mbar_wait(tfull_bar(acc), (tile_ctr >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * (BN / 2);
+                const uint32_t sc_addr = scale_smem + sl * kScaleTileBytes + half * (BN / 2) * 4;
+                const int lim_tile = (int)n_rows - (int)row0 - half * (BN / 2);  // valid columns of this half tile
+                // One 32-column chunk: s32 -> f32, times the row scale, 4 group maxima -> overall max; only groups that
+                // reach the threshold are examined element by element.  Survivors are parked in shared memory.
+                auto process = [&](const uint32_t (&v)[32], int c) {
+                    float f[32];
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; j4++) {
+                        float4 s4;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w)
+                                     : "r"(sc_addr + (uint32_t)(c * 32 + j4 * 4) * 4u));
+                        f[4 * j4 + 0] = __int2float_rn((int)v[4 * j4 + 0]) * s4.x;
+                        f[4 * j4 + 1] = __int2float_rn((int)v[4 * j4 + 1]) * s4.y;
+                        f[4 * j4 + 2] = __int2float_rn((int)v[4 * j4 + 2]) * s4.z;
+                        f[4 * j4 + 3] = __int2float_rn((int)v[4 * j4 + 3]) * s4.w;
+                    }
+                    float g[4];
+#pragma unroll
+                    for (int gi = 0; gi < 4; gi++) {
+                        float m0 = fmaxf(f[8 * gi], f[8 * gi + 1]);
+                        float m1 = fmaxf(f[8 * gi + 2], f[8 * gi + 3]);
+                        float m2 = fmaxf(f[8 * gi + 4], f[8 * gi + 5]);
+                        float m3 = fmaxf(f[8 * gi + 6], f[8 * gi + 7]);
+                        g[gi] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    }
+                    const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+                    if (q_valid && m >= thr) {
+#pragma unroll
+                        for (int gi = 0; gi < 4; gi++) {
+                            if (g[gi] >= thr) {
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {
+                                    const int i = 8 * gi + j;
+                                    if (f[i] >= thr && c * 32 + i < lim_tile) {
+                                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(stage_smem + (n_st * kEpiThreads + col) * 8),
+                                                     "r"(__float_as_uint(f[i])), "r"(row0 + half * (BN / 2) + c * 32 + i)
+                                                     : "memory");
+                                        if (++n_st == (uint32_t)kStageCap) {
+                                            flush_staged_i8(stage_smem, col, n_st, log_q, cnt_g + q, overflow_g + q, log_cap);
+                                            n_st = 0;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                };
+                uint32_t v0[32], v1[32];
+                tc_ld_32x32b_x32(taddr, v0);
+#pragma unroll 1
+                for (int c = 0; c < BN / 2 / 32; c += 2) {
+                    tc_wait_ld();
+                    tc_ld_32x32b_x32(taddr + (c + 1) * 32, v1);
+                    process(v0, c);
+                    tc_wait_ld();
+                    if (c + 2 < BN / 2 / 32) tc_ld_32x32b_x32(taddr + (c + 2) * 32, v0);
+                    process(v1, c + 1);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 2) mbar_arrive_cluster(acc ? tempty_lead1 : tempty_lead0);
+                    else mbar_arrive(tempty_bar(acc));
+                }
+                if (__any_sync(0xffffffffu, n_st >= (uint32_t)(kStageCap / 2))) {
+                    if (n_st) flush_staged_i8(stage_smem, col, n_st, log_q, cnt_g + q, overflow_g + q, log_cap);
+                    n_st = 0;
+                    __syncwarp();
+                }
+            }
+            if (n_st) {  // the next unit belongs to another query tile
+                flush_staged_i8(stage_smem, col, n_st, log_q, cnt_g + q, overflow_g + q, log_cap);
+                n_st = 0;
+            }
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all();
+    else __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        __syncwarp();
+        if constexpr (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
+    }
+}
+
+// ---- query preparation: f32 -> one int8 level hi (padded to whole tiles), s1, and the filter band e1 -----------
+__global__ void __launch_bounds__(128) prep_queries_i8_gemm_kernel(const float *__restrict__ q32, int n_queries,
+                                                                   int8_t *__restrict__ q8, float *__restrict__ s1_g,
+                                                                   float *__restrict__ e1_g) {
+    const int q = blockIdx.x;
+    __shared__ float red[4];
+    float x[3], amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        x[j] = q < n_queries ? q32[(size_t)q * kDim + threadIdx.x + 128 * j] : 0.f;
+        amax = fmaxf(amax, fabsf(x[j]));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    amax = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    const float s1 = amax > 0.f ? amax / 127.0f : 1.0f;
+    float err2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int hi = max(-127, min(127, (int)rintf(x[j] / s1)));
+        const float e = fmaf(-s1, (float)hi, x[j]);
+        err2 += e * e;
+        q8[(size_t)q * kDim + threadIdx.x + 128 * j] = (int8_t)hi;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = err2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s1_g[q] = s1;
+        // |sum (q_i - s1 hi_i) x_i| <= ||q - s1 hi|| * ||x||, dequantised rows have norm < 1.02; 1.03 also covers the f32
+        // rounding of this sum of squares; + 3e-6 for the f32 roundings of a = s1 * (s_row * HI) and of thr / s1.
+        e1_g[q] = sqrtf(red[0] + red[1] + red[2] + red[3]) * 1.03f + 3.0e-6f;
+    }
+}
+
+// ---- select: re-score the round's new log entries EXACTLY, keep the best k', publish the next threshold ----------
+// Entries [0, kept_g[q]) of the log carry exact scores from the previous select; entries [kept, cnt) were appended by
+// the round just finished and carry the filter's approximate value, which is ignored.  The exact score is the oracle's:
+// scale * (sequential f32 sum of q[i] * f32(x8[i])), oracle/dawn_oracle.c:dawn_oracle_search_i8 -- the same arithmetic
+// finalize.cu uses, so the final distances are bit-identical.
+__global__ void __launch_bounds__(kSelThreads) select_i8_kernel(uint2 *__restrict__ log_g, uint32_t *__restrict__ cnt_g,
+                                                                uint32_t *__restrict__ kept_g, float *__restrict__ thr_g,
+                                                                uint32_t *__restrict__ overflow_g, int log_cap, int kp,
+                                                                const uint8_t *__restrict__ arena,
+                                                                const float *__restrict__ q32, int n_queries,
+                                                                const float *__restrict__ s1_g, const float *__restrict__ e1_g,
+                                                                float limit_score, float eps_scale,
+                                                                const uint64_t *__restrict__ labels,
+                                                                Cand *__restrict__ final_lists) {
+    __shared__ unsigned long long keys[kSelCap];
+    __shared__ unsigned long long s_prefix;
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_need, s_out;
+    __shared__ __align__(16) float sq[kDim];
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    uint2 *log_q = log_g + (size_t)q * log_cap;
+    const uint32_t cnt = cnt_g[q];
+    const int n = (int)min(cnt, (uint32_t)log_cap);
+    const int kept = (int)min(kept_g[q], (uint32_t)n);
+    for (int c = tid; c < kDim; c += kSelThreads) sq[c] = q < n_queries ? q32[(size_t)q * kDim + c] : 0.f;
+    if (tid == 0) {
+        s_prefix = 0ull;
+        s_need = (uint32_t)kp;
+        s_out = 0u;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kSelThreads) {
+        const uint2 e = log_q[i];
+        float sc = __uint_as_float(e.x);
+        if (i >= kept) {  // exact re-score of a new entry
+            const uint4 *rp = reinterpret_cast<const uint4 *>(arena + i8_row_offset(e.y));
+            float acc = 0.0f;
+#pragma unroll 2
+            for (int c = 0; c < kDim / 16; c++) {
+                const uint4 u = __ldg(rp + c);
+                const int8_t *b8 = reinterpret_cast<const int8_t *>(&u);
+#pragma unroll
+                for (int j = 0; j < 16; j++) acc = __fadd_rn(acc, __fmul_rn(sq[c * 16 + j], (float)b8[j]));
+            }
+            sc = __fmul_rn(*reinterpret_cast<const float *>(arena + i8_scale_offset(e.y)), acc);
+        }
+        keys[i] = ((unsigned long long)float_to_ordered(sc) << 32) | (unsigned long long)(~e.y);
+    }
+    __syncthreads();
+    const unsigned long long K = n >= kp ? radix_select_kth(keys, n, kp, hist, &s_prefix, &s_need, tid) : 0ull;
+    for (int i = tid; i < n; i += kSelThreads) {
+        const unsigned long long key = keys[i];
+        if (key >= K) {
+            const uint32_t pos = atomicAdd(&s_out, 1u);
+            if (pos < (uint32_t)kp) {
+                const float sc = ordered_to_float((uint32_t)(key >> 32));
+                const uint32_t row = ~(uint32_t)key;
+                log_q[pos] = make_uint2(__float_as_uint(sc), row);
+                if (final_lists) {
+                    Cand c;
+                    c.score = sc;
+                    c.row = row;
+                    c.label = labels[row];
+                    final_lists[(size_t)q * kp + pos] = c;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int keep = min(n, kp);
+    if (final_lists)
+        for (int i = keep + tid; i < kp; i += kSelThreads) final_lists[(size_t)q * kp + i] = empty_cand();
+    if (tid == 0) {
+        cnt_g[q] = (uint32_t)keep;
+        kept_g[q] = (uint32_t)keep;
+        float T = n >= kp ? ordered_to_float((uint32_t)(K >> 32)) : __int_as_float(0xff800000);
+        // distance_limit pushed down: rows whose exact score is below limit_score are dropped by the caller anyway
+        if (limit_score > __int_as_float(0xff800000)) T = fmaxf(T, limit_score - 1e-6f);
+        // filter threshold in the epilogue's units (s_row * HI): a row with a < T - e1 has exact < T
+        const float s1 = q < n_queries ? s1_g[q] : 1.0f;
+        const float e1 = q < n_queries ? e1_g[q] * eps_scale : 0.f;
+        thr_g[q] = T > __int_as_float(0xff800000) ? (T - e1) / s1 - fabsf((T - e1) / s1) * 2.4e-7f : T;
+        if (cnt > (uint32_t)log_cap) overflow_g[q] = 1u;
+    }
+}
+
+// Blocked int8 arena as a 3-D tensor {384 B of a row, 8 rows of a block, blocks 3104 B apart}; box = 128 B x 8 x box_blocks
+// lands in shared memory as box_blocks*8 consecutive 128-byte rows = the canonical K-major SWIZZLE_128B operand layout.
+bool make_tmap_arena(CUtensorMap *map, const void *arena, uint64_t n_blocks, uint32_t box_blocks) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)kDim, (cuuint64_t)kI8BlockRows, (cuuint64_t)n_blocks};
+    cuuint64_t strides[2] = {(cuuint64_t)kDim, (cuuint64_t)kI8BlockBytes};
+    cuuint32_t box[3] = {(cuuint32_t)BKB, (cuuint32_t)kI8BlockRows, box_blocks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(arena), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// The 8 f32 scales behind each block's rows as a 2-D tensor {8 floats, blocks 3104 B apart}; box = 8 x 32 = one tile's 256 scales.
+bool make_tmap_scales(CUtensorMap *map, const void *arena, uint64_t n_blocks) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)kI8BlockRows, (cuuint64_t)n_blocks};
+    cuuint64_t strides[1] = {(cuuint64_t)kI8BlockBytes};
+    cuuint32_t box[2] = {(cuuint32_t)kI8BlockRows, (cuuint32_t)(BN / kI8BlockRows)};
+    cuuint32_t estr[2] = {1, 1};
+    const uint8_t *base = static_cast<const uint8_t *>(arena) + (size_t)kI8BlockRows * kDim;
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<uint8_t *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// hi queries [rows][384] int8 row-major, box = 128 B x 128 rows, 128 B swizzle
+bool make_tmap_q8(CUtensorMap *map, const void *base, uint64_t rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)kDim, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kDim};
+    cuuint32_t box[2] = {(cuuint32_t)BKB, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int CG>
+cudaError_t launch_round(int grid, cudaStream_t s, const CUtensorMap &tq, const CUtensorMap &tx, const CUtensorMap &ts,
+                         uint32_t tile_begin, uint32_t tile_end, uint32_t n_rows, uint32_t n_tiles_total, uint32_t perm_mult,
+                         int n_qtiles, int n_queries, int chunk, const float *thr, uint32_t *cnt, uint2 *log,
+                         uint32_t *overflow) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kI8Threads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int log_cap = kSelCap;
+    return cudaLaunchKernelEx(&cfg, gemm_i8_topk_kernel<CG>, tq, tx, ts, tile_begin, tile_end, n_rows, n_tiles_total, perm_mult,
+                              n_qtiles, n_queries, chunk, thr, cnt, log, overflow, log_cap);
+}
+
+}  // namespace
+
+size_t gemm_i8_workspace_bytes(int n_queries) {
+    const size_t qp = ((size_t)n_queries + 2 * BM - 1) / (2 * BM) * (2 * BM);
+    return qp * kDim + qp * (6 * sizeof(float)) + qp * (size_t)kSelCap * sizeof(uint2) + 1024;
+}
+
+cudaError_t launch_gemm_search_i8(const GemmSearchI8 &p, cudaStream_t s) {
+    if (p.n_queries <= 0 || p.n_rows == 0) return cudaErrorInvalidValue;
+    int cg = p.cta_group;
+    if (cg != 1 && cg != 2) cg = p.n_queries > BM ? 2 : 1;
+    if (p.grid % 2) cg = 1;
+    const int qtile = BM * cg;
+    const int qp = (p.n_queries + qtile - 1) / qtile * qtile;
+    const int n_qtiles = qp / qtile;
+    const int workers = p.grid / cg;
+    uint8_t *w = static_cast<uint8_t *>(p.workspace);
+    int8_t *q8 = reinterpret_cast<int8_t *>(w);
+    w += (size_t)qp * kDim;
+    float *s1 = reinterpret_cast<float *>(w);
+    w += (size_t)qp * sizeof(float);
+    float *e1 = reinterpret_cast<float *>(w);
+    w += (size_t)qp * sizeof(float);
+    float *thr = reinterpret_cast<float *>(w);
+    w += (size_t)qp * sizeof(float);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(w);
+    w += (size_t)qp * sizeof(uint32_t);
+    uint32_t *kept = reinterpret_cast<uint32_t *>(w);
+    w += (size_t)qp * sizeof(uint32_t);
+    uint32_t *overflow = reinterpret_cast<uint32_t *>(w);
+    w += (size_t)qp * sizeof(uint32_t);
+    w = reinterpret_cast<uint8_t *>(((uintptr_t)w + 255) & ~(uintptr_t)255);
+    uint2 *log = reinterpret_cast<uint2 *>(w);
+
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_i8_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gemm_i8_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const uint64_t n_blocks = (p.n_rows + kI8BlockRows - 1) / kI8BlockRows;
+    CUtensorMap tq, tx, ts;
+    if (!make_tmap_q8(&tq, q8, (uint64_t)qp) || !make_tmap_arena(&tx, p.arena, n_blocks, (uint32_t)(BN / cg / kI8BlockRows)) ||
+        !make_tmap_scales(&ts, p.arena, n_blocks))
+        return cudaErrorInvalidValue;
+
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(cnt, 0, (size_t)qp * 3 * sizeof(uint32_t), s)) != cudaSuccess) return e;  // cnt, kept, overflow
+    prep_queries_i8_gemm_kernel<<<qp, 128, 0, s>>>(p.queries, p.n_queries, q8, s1, e1);
+    // thresholds before the first round: -inf, or the pushed-down limit (a select pass over empty logs)
+    select_i8_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, kept, thr, overflow, kSelCap, p.kprime, p.arena, p.queries,
+                                                p.n_queries, s1, e1, p.limit_score, p.eps_scale, p.labels, nullptr);
+    int launches = 2;
+    // Rounds grow x8 (x4 for k' = 128): the filter band e1 lets ~2x more rows through than an exact threshold would,
+    // (growth - 1) * k' * 2.2 + k' entries must fit the 2048-entry log with margin.
+    uint64_t growth = p.kprime > 64 ? 4 : 8;
+    if (p.growth >= 2) growth = (uint64_t)p.growth;
+    while (growth > 2 && (growth - 1) * (uint64_t)p.kprime * 11 / 4 + (uint64_t)p.kprime > (uint64_t)kSelCap) growth /= 2;
+    const uint64_t total_tiles = (p.n_rows + BN - 1) / BN;
+    uint64_t mult = (uint64_t)((double)total_tiles * 0.6180339887498949) | 1ull;
+    auto gcd = [](uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; };
+    while (mult > 1 && gcd(mult, total_tiles) != 1) mult += 2;
+    if (total_tiles <= 2 || p.sequential_tiles) mult = 1;
+    mult %= total_tiles > 0 ? total_tiles : 1;
+    if (mult == 0) mult = 1;
+    uint64_t begin = 0, end = 1024 / BN;
+    while (begin < total_tiles) {
+        if (end > total_tiles || end + end / 4 > total_tiles) end = total_tiles;
+        const uint64_t n_tiles = end - begin;
+        uint64_t chunk = (n_tiles * (uint64_t)n_qtiles + (uint64_t)workers * 4 - 1) / ((uint64_t)workers * 4);
+        if (chunk < 1) chunk = 1;
+        if (chunk > 64) chunk = 64;
+        if (p.chunk_tiles > 0) chunk = (uint64_t)p.chunk_tiles;
+        if (cg == 2)
+            e = launch_round<2>(p.grid, s, tq, tx, ts, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows, (uint32_t)total_tiles,
+                                (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow);
+        else
+            e = launch_round<1>(p.grid, s, tq, tx, ts, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows, (uint32_t)total_tiles,
+                                (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow);
+        if (e != cudaSuccess) return e;
+        const bool last = end >= total_tiles;
+        select_i8_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, kept, thr, overflow, kSelCap, p.kprime, p.arena, p.queries,
+                                                    p.n_queries, s1, e1, p.limit_score, p.eps_scale, p.labels,
+                                                    last ? p.final_lists : nullptr);
+        launches += 2;
+        begin = end;
+        end = end * growth;
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (p.overflow_out) *p.overflow_out = overflow;
+    if (p.launches_out) *p.launches_out = launches;
+    return cudaSuccess;
+}
+
+}  // namespace dawn

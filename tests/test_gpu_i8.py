@@ -141,29 +141,62 @@ def test_i8_200k_rows(dawn, oracle):
         assert idx.profile()["uncertified"] == 0
 
 
-def test_i8_tensor_core_path_matches_oracle(dawn, oracle):
-    """Opt-in path for large batches over an int8 corpus (i8_tensor.cu): chunks dequantised to an fp16 scratch, the
-    tcgen05 rounds over each chunk, per-chunk candidate lists gathered, exact int8 re-score.  Labels and distances
-    must still be bit-identical to the int8 oracle, over several chunks and with ragged chunk sizes."""
-    n = 200_000
+@pytest.mark.parametrize("native", [1, 0])
+def test_i8_tensor_core_path_matches_oracle(dawn, oracle, native):
+    """Large batches over an int8 corpus on the tensor cores.  native = 1 (gemm_i8.cu, the default): tcgen05 kind::i8
+    straight from the blocked int8 arena with a one-level int8 query, every logged candidate re-scored exactly between
+    rounds.  native = 0 (i8_tensor.cu, the A/B partner): chunks dequantised to an fp16 scratch, the fp16 rounds over each
+    chunk, per-chunk lists gathered.  Either way labels and distances must be bit-identical to the int8 oracle, with
+    ragged sizes, a query batch that is not a multiple of the tile, and both CTA-pair and one-CTA tiles."""
+    n = 200_003
     with dawn.new_index(i8_options(dawn, capacity=n)) as idx:
         idx.add_synthetic(SEED, 0, n)
-        f32 = np.concatenate([oracle.np_synth_rows_f32(SEED, i, 20000) for i in range(0, n, 20000)])
+        f32 = np.concatenate([oracle.np_synth_rows_f32(SEED, i, min(20000, n - i)) for i in range(0, n, 20000)])
         q8, sc = oracle.store_i8(f32)
-        qs = oracle.make_queries(SEED, 33, 40, n)
+        idx.set_option("i8_native", native)
         idx.set_option("i8_tensor_min_batch", 8)
-        idx.set_option("i8_tensor_chunk_rows", 65536)  # 4 chunks of 50,176 / 50,176 / 50,176 / 49,472 rows
-        for k in (10, 100):
-            before = idx.profile()
-            gl, gd, cnt = idx.search_batch(qs, k)
-            after = idx.profile()
-            assert after["gemm_batches"] - before["gemm_batches"] == 4  # one run of the rounds per chunk
-            for i, q in enumerate(qs):
-                wl, wd = oracle.search_i8(q8, sc, None, q, k)
-                assert cnt[i] == k
-                assert (gl[i] == wl).all() and (bits(gd[i]) == bits(wd)).all(), (k, i)
+        idx.set_option("i8_tensor_chunk_rows", 65536)  # native = 0: 4 chunks
+        for nq in (40, 130):                           # one 128-query tile (one CTA per tile) / CTA pairs
+            qs = oracle.make_queries(SEED, 33 + nq, nq, n)
+            for k in (10, 100):
+                before = idx.profile()
+                gl, gd, cnt = idx.search_batch(qs, k)
+                after = idx.profile()
+                assert after["gemm_batches"] - before["gemm_batches"] == (1 if native else 4)
+                assert after["escalations"] == before["escalations"]
+                for i, q in enumerate(qs):
+                    wl, wd = oracle.search_i8(q8, sc, None, q, k)
+                    assert cnt[i] == k
+                    assert (gl[i] == wl).all() and (bits(gd[i]) == bits(wd)).all(), (native, nq, k, i)
         assert idx.profile()["uncertified"] == 0
         # below the batch threshold the scan path answers, with the same result
         m = idx.search(qs[0], 10)
         wl, wd = oracle.search_i8(q8, sc, None, qs[0], 10)
         assert (m.labels == wl).all() and (bits(m.distances) == bits(wd)).all()
+
+
+def test_i8_native_tensor_path_ties_limit_and_small_corpus(dawn, oracle):
+    """kind::i8 path corner cases: exact duplicates (ties break on the label; the overflowing candidate log escalates to the
+    exact scan), a pushed-down distance limit, and a corpus smaller than one round."""
+    n = 70_000
+    f32 = oracle.np_synth_rows_f32(SEED + 9, 0, n).copy()
+    f32[1000:1300] = f32[999]                                # 301 identical pages
+    labels = np.arange(1, n + 1, dtype=np.uint64)
+    q8, sc = oracle.store_i8(f32)
+    with dawn.new_index(i8_options(dawn, capacity=n)) as idx:
+        idx.add_batch(labels, f32)
+        idx.set_option("i8_tensor_min_batch", 4)
+        qs = np.concatenate([f32[999:1000], oracle.make_queries(SEED + 9, 5, 19, n)])
+        for k in (10, 100):
+            gl, gd, cnt = idx.search_batch(qs, k)
+            for i, q in enumerate(qs):
+                wl, wd = oracle.search_i8(q8, sc, labels, q, k)
+                assert (gl[i] == wl).all() and (bits(gd[i]) == bits(wd)).all(), (k, i)
+        assert idx.profile()["gemm_batches"] >= 2
+        wl, wd = oracle.search_i8(q8, sc, labels, qs[3], 20)
+        for lim in (float(wd[5]), float(wd[-1]) + 0.3, 0.0):
+            gl, gd, cnt = idx.search_batch_limit(qs, 20, lim)
+            for i, q in enumerate(qs):
+                wl, wd = oracle.search_i8(q8, sc, labels, q, 20)
+                keep = int((wd < np.float32(lim)).sum())
+                assert cnt[i] == keep and (gl[i][:keep] == wl[:keep]).all() and (bits(gd[i][:keep]) == bits(wd[:keep])).all()
