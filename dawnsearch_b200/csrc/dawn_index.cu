@@ -711,6 +711,14 @@ int search_i8_native(dawn_index *idx, SearchWs *ws, const float *d_queries, size
                      uint32_t *d_status_out) {
     const size_t qp = (batch + 255) / 256 * 256;
     int rc;
+    // The rounds rank EXACT scores, so no slack is needed for the certificate beyond "the k'-th is strictly worse than
+    // the k-th": k' = k + 4 (rounded up to 4, at least 16) instead of the scan paths' 16/32/64/128 -- fewer survivors per
+    // round to log and re-score (k = 100: 104 instead of 128).
+    {
+        int kp = ((int)k + 4 + 3) / 4 * 4;
+        if (kp < 16) kp = 16;
+        if (kp < kprime) kprime = kp;
+    }
     if ((rc = ensure_gemm_ws(idx, ws, gemm_i8_workspace_bytes((int)batch)))) return rc;
     if ((rc = ensure_dev(idx, &ws->d_partials, &ws->partials_cap, qp * kprime))) return rc;
     if ((rc = prepare_counters(idx, ws, 1, s))) return rc;

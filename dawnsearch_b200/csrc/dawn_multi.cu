@@ -26,13 +26,66 @@
 #include <vector>
 
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is bound at run time, see NcclApi
 
 #include "../../include/dawn_index.h"
 
 namespace {
 
 thread_local std::string g_multi_err;
+
+// NCCL is bound at RUN time (dlopen) instead of through a DT_NEEDED entry, for two reasons:
+//  * a process that already holds an NCCL must keep using THAT one.  The test / bench harness imports torch, whose
+//    libtorch_cuda.so needs its own bundled libnccl.so.2 (2.28, with symbols the system 2.27 lacks); the dynamic loader
+//    matches by SONAME, so whichever libnccl.so.2 is mapped first serves everybody -- a DT_NEEDED on the system copy made
+//    `import torch` fail with "undefined symbol: ncclDevCommCreate" whenever libdawn_b200.so happened to be loaded first;
+//  * single-GPU users of the library need no NCCL at all.
+// Resolution order: an NCCL already mapped into the process, then $DAWN_NCCL_LIB, then "libnccl.so.2" by name.
+struct NcclApi {
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int *) = nullptr;
+    std::string origin;
+    bool ok = false;
+};
+
+const NcclApi &nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        a.origin = "already loaded in the process";
+        if (!h) {
+            if (const char *env = getenv("DAWN_NCCL_LIB")) {
+                h = dlopen(env, RTLD_NOW | RTLD_LOCAL);
+                a.origin = env;
+            }
+        }
+        if (!h) {
+            h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+            a.origin = "libnccl.so.2";
+        }
+        if (!h) {
+            a.origin = std::string("libnccl.so.2 cannot be loaded: ") + (dlerror() ? dlerror() : "?");
+            return a;
+        }
+        a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(dlsym(h, "ncclCommInitAll"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+        a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(h, "ncclGroupStart"));
+        a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+        a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+        a.GetVersion = reinterpret_cast<decltype(a.GetVersion)>(dlsym(h, "ncclGetVersion"));
+        a.ok = a.CommInitAll && a.CommDestroy && a.GroupStart && a.GroupEnd && a.AllGather && a.GetErrorString;
+        if (!a.ok) a.origin += " (required symbols missing)";
+        return a;
+    }();
+    return api;
+}
 
 struct Shard {
     int device = 0;
@@ -185,10 +238,16 @@ int dawn_multi_create(const int *devices, size_t n_devices, uint32_t scalar, daw
         for (size_t b = a + 1; b < n_devices; b++)
             if (devices[a] == devices[b]) distinct = false;
     if (distinct && !getenv("DAWN_MULTI_NO_NCCL")) {
+        const NcclApi &nccl = nccl_api();
+        if (!nccl.ok) {  // several GPUs were asked for and the exchange they need is missing: fail loudly, no silent peer-copy fallback
+            g_multi_err = "NCCL is required for a multi-GPU handle: " + nccl.origin;
+            dawn_multi_free(m);
+            return DAWN_ERR_CUDA;
+        }
         std::vector<ncclComm_t> comms(n_devices);
-        ncclResult_t nr = ncclCommInitAll(comms.data(), (int)n_devices, devices);
+        ncclResult_t nr = nccl.CommInitAll(comms.data(), (int)n_devices, devices);
         if (nr != ncclSuccess) {
-            g_multi_err = std::string("ncclCommInitAll: ") + ncclGetErrorString(nr);
+            g_multi_err = std::string("ncclCommInitAll: ") + nccl.GetErrorString(nr);
             dawn_multi_free(m);
             return DAWN_ERR_CUDA;
         }
@@ -211,7 +270,7 @@ void dawn_multi_free(dawn_multi *m) {
             s->th.join();
         }
         cudaSetDevice(s->device);
-        if (s->comm) ncclCommDestroy(s->comm);
+        if (s->comm) nccl_api().CommDestroy(s->comm);
         if (s->ev_a) cudaEventDestroy(s->ev_a);
         if (s->ev_b) cudaEventDestroy(s->ev_b);
         cudaFree(s->d_gather);
@@ -442,15 +501,16 @@ int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, s
     if (use_nccl) {
         // THE exchange: one all-gather of the packed blocks, issued for every shard's communicator as one group
         // (every shard's stream is idle here, so the collective starts at once on all GPUs)
-        ncclResult_t nr = ncclGroupStart();
+        const NcclApi &nccl = nccl_api();
+        ncclResult_t nr = nccl.GroupStart();
         for (size_t g = 0; g < G && nr == ncclSuccess; g++) {
             Shard *s = m->shards[g];
-            nr = ncclAllGather(s->d_block, s->d_gather, bb, ncclUint8, s->comm, s->stream);
+            nr = nccl.AllGather(s->d_block, s->d_gather, bb, ncclUint8, s->comm, s->stream);
         }
-        ncclResult_t ne = ncclGroupEnd();
+        ncclResult_t ne = nccl.GroupEnd();
         if (nr == ncclSuccess) nr = ne;
         if (nr != ncclSuccess) {
-            g_multi_err = std::string("ncclAllGather: ") + ncclGetErrorString(nr);
+            g_multi_err = std::string("ncclAllGather: ") + nccl.GetErrorString(nr);
             return DAWN_ERR_CUDA;
         }
         m->nccl_exchanges++;

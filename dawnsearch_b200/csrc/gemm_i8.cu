@@ -61,7 +61,8 @@ constexpr int kStagingBytes = kStageCap * kEpiThreads * 8;  // 32 KB
 constexpr int kScaleSlots = 8;      // scale tiles in flight; the producer runs at most 4 tiles ahead of the epilogue
 constexpr int kScaleTileBytes = BN * 4;
 constexpr int kBarBytes = 512;
-constexpr int kSmemBytes = 1024 + kABytes + kBRingBytes + kBarBytes + kScaleSlots * kScaleTileBytes + kStagingBytes;
+constexpr int kGroupMaxBytes = kEpiWarps * 32 * 4;  // per epilogue warp: the largest scale of each group of 4 columns
+constexpr int kSmemBytes = 1024 + kABytes + kBRingBytes + kBarBytes + kScaleSlots * kScaleTileBytes + kStagingBytes + kGroupMaxBytes;
 
 // Instruction descriptor for kind::i8: D = s32 (c_format 2 at bit 4), A = B = signed int8 (format 1 at bits 7 and 10),
 // both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
@@ -75,6 +76,7 @@ struct I8Smem {  // offsets from the 1024-aligned base
     static constexpr int bar_off = kABytes + kBRingBytes;
     static constexpr int scale_off = bar_off + kBarBytes;
     static constexpr int staging_off = scale_off + kScaleSlots * kScaleTileBytes;
+    static constexpr int groupmax_off = staging_off + kStagingBytes;
     // barriers (8 B each): full[6], empty[6], tmem_full[2], tmem_empty[2], a_full, a_free, scale_full[8]; then tmem ptr
 };
 
@@ -154,9 +156,12 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
     // Work units and the strided visiting permutation: as in gemm_topk.cu.
+    // (the 64-bit modulo is taken once per work unit; inside a unit the physical tile advances by perm_mult mod total)
     const uint32_t n_tiles = tile_end - tile_begin;
-    auto phys_row0 = [&](uint32_t tile) {
-        return (uint32_t)(((uint64_t)(tile_begin + tile) * perm_mult) % n_tiles_total) * (uint32_t)BN;
+    auto phys_tile = [&](uint32_t tile) { return (uint32_t)(((uint64_t)(tile_begin + tile) * perm_mult) % n_tiles_total); };
+    auto phys_next = [&](uint32_t pt) {
+        const uint32_t nx = pt + perm_mult;  // perm_mult < n_tiles_total <= 2^24: no overflow
+        return nx >= n_tiles_total ? nx - n_tiles_total : nx;
     };
     const uint32_t n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
     const uint32_t n_units = n_chunks * (uint32_t)n_qtiles;
@@ -186,8 +191,9 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
             const uint32_t tile0 = chunk * chunk_tiles;
             const uint32_t tile1 = min(n_tiles, tile0 + chunk_tiles);
-            for (uint32_t tile = tile0; tile < tile1; tile++, tile_ctr++) {
-                const uint32_t prow0 = phys_row0(tile);
+            uint32_t pt = phys_tile(tile0);
+            for (uint32_t tile = tile0; tile < tile1; tile++, tile_ctr++, pt = phys_next(pt)) {
+                const uint32_t prow0 = pt * (uint32_t)BN;
                 // The whole tile's 256 scales for THIS CTA's epilogue (each CTA of a pair filters all 256 columns
                 // for its own 128 queries).  The slot being overwritten belonged to the tile 8 back; the B ring and
                 // the two accumulators keep this producer at most 4 tiles ahead of the epilogue, so it is free.
@@ -258,11 +264,18 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: scale, threshold filter =====================
+        // ===================== epilogue: threshold filter =====================
+        // The test per element is  s_row * HI >= thr  (thr in units of s_row * HI, one per query = per thread).  Doing that
+        // for every element costs I2F + FMUL + FMNMX each -- the first ncu capture had the tensor pipe 42 % busy waiting for
+        // this.  Instead the test is hierarchical on INTEGER maxima: for a set S of columns, max_S(HI) * max_S(s_row) >= thr is
+        // implied by any element of S passing (thr > 0, scales > 0).  Level 1: a 32-column chunk (16 three-input integer
+        // maxima + one compare); level 2, only in chunks that pass: its 8 groups of 4 columns; level 3, only in groups that
+        // pass: the 4 elements, exactly.  Once the thresholds have tightened almost every chunk stops at level 1.
         const int quarter = warp & 3;          // TMEM lane quarter this warp may read
         const int half = (warp - 4) >> 2;      // which 128 of the tile's 256 columns this warp filters
         const int col = (warp - 4) * 32 + lane;  // this thread's column in the staging area
         const uint32_t stage_smem = base + I8Smem::staging_off;
+        const uint32_t gmax_smem = base + I8Smem::groupmax_off + (uint32_t)(warp - 4) * 128u;
         uint32_t n_st = 0;
         uint32_t tile_ctr = 0;
         const uint32_t tempty_lead0 = CG == 2 ? mapa_rank(tempty_bar(0), 0) : 0u;
@@ -273,64 +286,78 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const int q = t * BM * CG + (int)cta_rank * BM + quarter * 32 + lane;
             const bool q_valid = q < n_queries;
             const float thr = q_valid ? thr_g[q] : __int_as_float(0x7f800000);  // in units of s_row * HI
+            const bool thr_pos = thr > 0.0f;  // the chunk bound needs a positive threshold (round 0 starts at -inf)
             uint2 *log_q = log_g + (size_t)q * log_cap;
             const uint32_t tile0 = chunk * chunk_tiles;
             const uint32_t tile1 = min(n_tiles, tile0 + chunk_tiles);
-            for (uint32_t tile = tile0; tile < tile1; tile++, tile_ctr++) {
+            uint32_t pt = phys_tile(tile0);
+            for (uint32_t tile = tile0; tile < tile1; tile++, tile_ctr++, pt = phys_next(pt)) {
                 const uint32_t acc = tile_ctr & 1u;
-                const uint32_t row0 = phys_row0(tile);
+                const uint32_t row0 = pt * (uint32_t)BN;
                 const uint32_t sl = tile_ctr % kScaleSlots;
+                const uint32_t sc_addr = scale_smem + sl * kScaleTileBytes + half * (BN / 2) * 4;
                 mbar_wait(sfull_bar(sl), (tile_ctr / kScaleSlots) & 1u);
+                // largest scale of each group of 4 columns (lane l: columns 4l..4l+3 of this half tile) -> this warp's
+                // shared array, and of each 32-column chunk (8 lanes) -> register
+                float smax;
+                {
+                    float4 s4;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w)
+                                 : "r"(sc_addr + (uint32_t)lane * 16u));
+                    smax = fmaxf(fmaxf(s4.x, s4.y), fmaxf(s4.z, s4.w));
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(gmax_smem + (uint32_t)lane * 4u), "f"(smax) : "memory");
+                    smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, 1));
+                    smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, 2));
+                    smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, 4));  // every lane of group l/8 holds chunk l/8's max
+                    __syncwarp();
+                }
                 mbar_wait(tfull_bar(acc), (tile_ctr >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * (BN / 2);
-                const uint32_t sc_addr = scale_smem + sl * kScaleTileBytes + half * (BN / 2) * 4;
                 const int lim_tile = (int)n_rows - (int)row0 - half * (BN / 2);  // valid columns of this half tile
-                // One 32-column chunk: s32 -> f32, times the row scale, 4 group maxima -> overall max; only groups that
-                // reach the threshold are examined element by element.  Survivors are parked in shared memory.
-                auto process = [&](const uint32_t (&v)[32], int c) {
-                    float f[32];
+                // levels 2 and 3 for one chunk (rare once thresholds are tight)
+                auto examine = [&](const uint32_t (&v)[32], const int (&m)[8], int c) {
+                    float gs[8];
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(gs[0]), "=f"(gs[1]), "=f"(gs[2]), "=f"(gs[3])
+                                 : "r"(gmax_smem + (uint32_t)c * 32u));
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(gs[4]), "=f"(gs[5]), "=f"(gs[6]), "=f"(gs[7])
+                                 : "r"(gmax_smem + (uint32_t)c * 32u + 16u));
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; j4++) {
+                    for (int g = 0; g < 8; g++) {
+                        if (thr_pos && !(__int2float_rn(m[g]) * gs[g] >= thr)) continue;
                         float4 s4;
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                      : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w)
-                                     : "r"(sc_addr + (uint32_t)(c * 32 + j4 * 4) * 4u));
-                        f[4 * j4 + 0] = __int2float_rn((int)v[4 * j4 + 0]) * s4.x;
-                        f[4 * j4 + 1] = __int2float_rn((int)v[4 * j4 + 1]) * s4.y;
-                        f[4 * j4 + 2] = __int2float_rn((int)v[4 * j4 + 2]) * s4.z;
-                        f[4 * j4 + 3] = __int2float_rn((int)v[4 * j4 + 3]) * s4.w;
-                    }
-                    float g[4];
+                                     : "r"(sc_addr + (uint32_t)(c * 32 + g * 4) * 4u));
+                        const float sc[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-                    for (int gi = 0; gi < 4; gi++) {
-                        float m0 = fmaxf(f[8 * gi], f[8 * gi + 1]);
-                        float m1 = fmaxf(f[8 * gi + 2], f[8 * gi + 3]);
-                        float m2 = fmaxf(f[8 * gi + 4], f[8 * gi + 5]);
-                        float m3 = fmaxf(f[8 * gi + 6], f[8 * gi + 7]);
-                        g[gi] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                    }
-                    const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-                    if (q_valid && m >= thr) {
-#pragma unroll
-                        for (int gi = 0; gi < 4; gi++) {
-                            if (g[gi] >= thr) {
-#pragma unroll
-                                for (int j = 0; j < 8; j++) {
-                                    const int i = 8 * gi + j;
-                                    if (f[i] >= thr && c * 32 + i < lim_tile) {
-                                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(stage_smem + (n_st * kEpiThreads + col) * 8),
-                                                     "r"(__float_as_uint(f[i])), "r"(row0 + half * (BN / 2) + c * 32 + i)
-                                                     : "memory");
-                                        if (++n_st == (uint32_t)kStageCap) {
-                                            flush_staged_i8(stage_smem, col, n_st, log_q, cnt_g + q, overflow_g + q, log_cap);
-                                            n_st = 0;
-                                        }
-                                    }
+                        for (int j = 0; j < 4; j++) {
+                            const int i = 4 * g + j;
+                            const float f = __int2float_rn((int)v[i]) * sc[j];
+                            if (f >= thr && c * 32 + i < lim_tile) {
+                                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(stage_smem + (n_st * kEpiThreads + col) * 8),
+                                             "r"(__float_as_uint(f)), "r"(row0 + half * (BN / 2) + c * 32 + i)
+                                             : "memory");
+                                if (++n_st == (uint32_t)kStageCap) {
+                                    flush_staged_i8(stage_smem, col, n_st, log_q, cnt_g + q, overflow_g + q, log_cap);
+                                    n_st = 0;
                                 }
                             }
                         }
                     }
+                };
+                auto process = [&](const uint32_t (&v)[32], int c) {
+                    int m[8];
+#pragma unroll
+                    for (int g = 0; g < 8; g++)
+                        m[g] = max(max((int)v[4 * g], (int)v[4 * g + 1]), max((int)v[4 * g + 2], (int)v[4 * g + 3]));
+                    const int mm = max(max(max(m[0], m[1]), max(m[2], m[3])), max(max(m[4], m[5]), max(m[6], m[7])));
+                    const float sm_c = __shfl_sync(0xffffffffu, smax, 8 * c);
+                    const bool hit = q_valid && (!thr_pos || __int2float_rn(mm) * sm_c >= thr);
+                    if (hit) examine(v, m, c);
                     __syncwarp();
                 };
                 uint32_t v0[32], v1[32];

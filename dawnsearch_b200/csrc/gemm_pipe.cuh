@@ -88,8 +88,17 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Arrival on a barrier of another CTA of the cluster (the epilogue warps of a CTA pair tell the leader's MMA issuer that a
+// TMEM accumulator may be overwritten).  Default semantics (.release at CTA scope), the form CUTLASS's ClusterBarrier::arrive
+// uses: what has to be ordered before the arrival are this warp's tcgen05.ld's, and tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync do that.  The former .release.cluster cost a MEMBAR.ALL.GPU + ERRBAR per tile per warp --
+// 25 % of the epilogue warps' stall samples in the first ncu capture of gemm_i8_topk_kernel (profiles/r02_*).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#ifdef DAWN_ARRIVE_RELEASE_CLUSTER  // A/B builds only (make OUT=../lib_ab EXTRA=-DDAWN_ARRIVE_RELEASE_CLUSTER)
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 // TMA load issued by either CTA of a pair; completion bytes are counted on the LEADER's barrier.
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1,

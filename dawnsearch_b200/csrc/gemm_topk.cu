@@ -150,8 +150,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // perm_mult coprime to n_tiles_total): every round is a uniform sample of the whole corpus, so the
     // thresholds learnt in early rounds are representative whatever order the pages were stored in.
     const uint32_t n_tiles = tile_end - tile_begin;
-    auto phys_row0 = [&](uint32_t tile) {
-        return (uint32_t)(((uint64_t)(tile_begin + tile) * perm_mult) % n_tiles_total) * (uint32_t)BN;
+    // (the 64-bit modulo is taken once per work unit; inside a unit the physical tile advances by perm_mult mod total)
+    auto phys_tile = [&](uint32_t tile) { return (uint32_t)(((uint64_t)(tile_begin + tile) * perm_mult) % n_tiles_total); };
+    auto phys_next = [&](uint32_t pt) {
+        const uint32_t nx = pt + perm_mult;  // perm_mult < n_tiles_total <= 2^24: no overflow
+        return nx >= n_tiles_total ? nx - n_tiles_total : nx;
     };
     const uint32_t n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
     const uint32_t n_units = n_chunks * (uint32_t)n_qtiles;
@@ -187,8 +190,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
             const uint32_t tile0 = chunk * chunk_tiles;
             const uint32_t tile1 = min(n_tiles, tile0 + chunk_tiles);
-            for (uint32_t tile = tile0; tile < tile1; tile++) {
-                const int row0 = (int)phys_row0(tile) + (int)cta_rank * kBRows;
+            uint32_t pt = phys_tile(tile0);
+            for (uint32_t tile = tile0; tile < tile1; tile++, pt = phys_next(pt)) {
+                const int row0 = (int)(pt * (uint32_t)BN) + (int)cta_rank * kBRows;
                 for (int kb = 0; kb < kKBlocks; kb++, g++) {
                     const uint32_t s = g % kStagesB;
                     mbar_wait(empty_bar(s), ((g / kStagesB) & 1u) ^ 1u);
@@ -267,9 +271,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             uint2 *log_q = log_g + (size_t)q * log_cap;
             const uint32_t tile0 = chunk * chunk_tiles;
             const uint32_t tile1 = min(n_tiles, tile0 + chunk_tiles);
-            for (uint32_t tile = tile0; tile < tile1; tile++, tile_ctr++) {
+            uint32_t pt = phys_tile(tile0);
+            for (uint32_t tile = tile0; tile < tile1; tile++, tile_ctr++, pt = phys_next(pt)) {
                 const uint32_t acc = tile_ctr & 1u;
-                const uint32_t row0 = phys_row0(tile);
+                const uint32_t row0 = pt * (uint32_t)BN;
                 mbar_wait(tfull_bar(acc), (tile_ctr >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;

@@ -444,6 +444,13 @@ class MultiIndex:
     first device (include/dawn_index.h: dawn_multi_*).  Same method names as `Index`."""
 
     def __init__(self, devices, quantization: int = ScalarKind.F16):
+        # The library binds NCCL at run time and prefers one that is already mapped.  In a Python process that will also
+        # import torch, torch's bundled NCCL has to be the one: it is newer than the system copy and the dynamic loader
+        # shares libnccl.so.2 by SONAME.  (A Rust / C++ host has no such concern.)
+        if len(set(devices)) > 1:
+            import importlib.util
+            if importlib.util.find_spec("torch") is not None:
+                import torch  # noqa: F401
         self._L = load_library()
         dev = (C.c_int * len(devices))(*devices)
         h = _vp()

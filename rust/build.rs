@@ -5,7 +5,7 @@
 // UNCOMPILED IN THIS REPO: the build image has no cargo/rustc.  What IS checked here, on every CPU test run
 // (tests/test_rust_shim.py): the source list below equals `SRCS` of dawnsearch_b200/csrc/Makefile, the nvcc
 // flags equal the Makefile's `NVCCFLAGS` (minus -Xptxas -v), every `extern "C"` name in gpu_index.rs is
-// declared in include/dawn_index.h and exported by the built library, and the link line carries NCCL.
+// declared in include/dawn_index.h and exported by the built library, and the link line matches the Makefile's.
 use std::{env, path::PathBuf, process::Command};
 
 // keep in sync with SRCS in dawnsearch_b200/csrc/Makefile (enforced by tests/test_rust_shim.py)
@@ -44,7 +44,8 @@ fn main() {
     println!("cargo:rustc-link-lib=static=dawn_b200");
     println!("cargo:rustc-link-search=native={cuda}/lib64");
     println!("cargo:rustc-link-lib=static=cudart_static");
-    println!("cargo:rustc-link-lib=dylib=nccl");       // dawn_multi.cu: ncclCommInitAll / ncclAllGather
+    // NCCL (dawn_multi.cu: ncclCommInitAll / ncclAllGather) is bound at run time with dlopen("libnccl.so.2"), so that a
+    // process which already maps an NCCL keeps using that one; -ldl below is all the link line needs for it.
     println!("cargo:rustc-link-lib=dylib=stdc++");
     println!("cargo:rustc-link-lib=dylib=pthread");
     println!("cargo:rustc-link-lib=dylib=dl");

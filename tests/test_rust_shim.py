@@ -1,6 +1,6 @@
 """The Rust side cannot be compiled here (no cargo/rustc in the image), so these CPU tests pin the things a
 build would trip over: build.rs compiles exactly the Makefile's sources with the Makefile's flags and links
-NCCL, and every `extern "C"` name the shim binds is declared in include/dawn_index.h and exported by the
+the same libraries, and every `extern "C"` name the shim binds is declared in include/dawn_index.h and exported by the
 built library (north_star (1); replaces Cargo.toml:36-38 / search_provider.rs:32 of the reference)."""
 import os
 import re
@@ -33,8 +33,8 @@ def test_build_rs_compiles_every_source_of_the_makefile():
     assert on_disk == sorted(srcs), "a .cu file in csrc/ is missing from the Makefile (and build.rs)"
 
 
-def test_build_rs_uses_the_makefile_flags_and_links_nccl():
-    flags = [f for f in _makefile_var("NVCCFLAGS") if f != "$(ARCH)"]
+def test_build_rs_uses_the_makefile_flags_and_link_line():
+    flags = [f for f in _makefile_var("NVCCFLAGS") if f not in ("$(ARCH)", "$(EXTRA)")]  # EXTRA: empty unless an A/B build asks
     arch = _makefile_var("ARCH")
     want = arch + flags
     # -Xptxas -v only produces the register report the Makefile archives
@@ -45,7 +45,16 @@ def test_build_rs_uses_the_makefile_flags_and_links_nccl():
     mk = open(os.path.join(ROOT, "dawnsearch_b200", "csrc", "Makefile")).read()
     for lib in re.findall(r"-l(\w+)", mk.split("-shared", 1)[1]):
         assert lib in link, f"Makefile links -l{lib}, build.rs does not"
-    assert "nccl" in link
+    # NCCL is bound at run time (dlopen in dawn_multi.cu: a DT_NEEDED on the system libnccl.so.2 clashes with the copy
+    # torch bundles), so neither link line names it, and the library must not carry it as a dependency
+    assert "nccl" not in link and "dl" in link
+    assert "dlopen(\"libnccl.so.2\"" in open(os.path.join(ROOT, "dawnsearch_b200", "csrc", "dawn_multi.cu")).read()
+
+
+def test_library_has_no_load_time_dependency_on_nccl(dawn):
+    out = subprocess.run(["readelf", "-d", dawn.index.LIB_PATH], capture_output=True, text=True).stdout
+    needed = re.findall(r"\(NEEDED\).*\[(.*?)\]", out)
+    assert needed and not any("nccl" in n for n in needed), needed
 
 
 def test_every_symbol_the_shim_binds_exists(dawn):
