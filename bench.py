@@ -357,6 +357,17 @@ def run_ours(args):
             gms = prof["gemm_ms"] / int(prof["gemm_batches"])
             flops = 2.0 * batch * n_local * DIM
             ach = flops / (gms / 1e3) / 1e12
+            if args.scalar == "i8":
+                # int8 tensor path (tcgen05 kind::i8): MEASURED_PEAKS.json holds no int8 figure; the int8 pipe is specified at
+                # twice the bf16 rate (4.5 vs 2.25 POP/s dense), so the denominator is 2 x the measured sustained bf16 peak
+                peak = 2.0 * peaks["tf_sustained"]
+                ratio = ncu_traffic_ratio("gemm_i8_topk_kernel<2> final round")
+                return {"bound": "tensor", "kernel": "gemm_i8_topk_kernel (tcgen05 kind::i8; all rounds of a batch incl. the exact re-score selects)",
+                        "achieved": ach, "peak": peak, "unit": "TOP/s (int8)", "frac": ach / peak,
+                        "traffic": ratio * n_local * row_bytes if ratio else None,
+                        "peak_source": "2 x " + peaks["source"] + " bf16_tflops_sustained (no measured int8 peak on this pool; the int8 pipe is rated at 2x bf16)",
+                        "frac_of_nominal_4500": ach / 4500.0, "algorithmic_ops_per_batch": flops, "avg_batch_ms": gms,
+                        "corpus_stream_gbps": n_local * row_bytes / (gms / 1e3) / 1e9}
             ratio = ncu_traffic_ratio("gemm_topk_kernel<2> final round")
             return {"bound": "tensor", "kernel": "gemm_topk_kernel (tcgen05; all rounds of a batch incl. select)",
                     "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
@@ -490,7 +501,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f16 x f16 -> f32 (tensor cores) / f32 scan, exact f32 re-score",
+            "scaling": "strong", "vs_baseline": None, "dtype": ("f16 x f16 -> f32 (tensor cores) / f32 scan, exact f32 re-score" if args.scalar == "f16" else
+                                                          "s8 x s8 -> s32 (tensor cores) / dp4a scan, exact f32 re-score"),
             "data": "synthetic",
             "config": {"workload": workload_name(args), "rows": args.rows, "rows_per_gpu": n_local,
                        "batch": B, "k": k, "l2": "inputs larger than L2 (corpus shard >> 126 MB), no flush",

@@ -4,8 +4,8 @@ Only the hot path lives here: `csrc/` (hand-written sm_100a kernels + the C ABI 
 include/dawn_index.h) and `index.py`, a ctypes mirror of the `usearch::ffi::Index` surface the
 reference calls (src/search/search_provider.rs).  There is no CPU fallback.
 """
-from .index import (EM_LEN, MAX_K, Batcher, DawnError, Index, IndexOptions, Matches, MetricKind, MultiIndex, ScalarKind,
+from .index import (EM_LEN, MAX_K, Batcher, DawnError, Index, IndexOptions, Matches, MetricKind, MultiIndex, ScalarKind, ScoreError,
                     decode_i24, encode_i24, is_normalized, load_library, merge_results_device, new_index, normalize)
 
 __all__ = ["EM_LEN", "MAX_K", "Batcher", "decode_i24", "encode_i24", "is_normalized", "normalize", "DawnError", "Index", "IndexOptions", "Matches", "MetricKind", "MultiIndex",
-           "ScalarKind", "load_library", "merge_results_device", "new_index"]
+           "ScalarKind", "ScoreError", "load_library", "merge_results_device", "new_index"]

@@ -129,8 +129,15 @@ struct FinalizeLaunch {
     int n_counters;
     uint32_t *status_out;   // optional: receives counters[0] (scan status) before the reset
     float eps_scale;        // multiplies every eps: > 1 when stored rows are longer than the reference's norm gate allows
-    uint32_t *stats;        // optional device words: [0] += queries left uncertified, [1] |= scan status
+    uint32_t *stats;        // optional device words: [0] += queries left uncertified, [1] |= scan status,
+                            // [2] = max over every finalized candidate of |selection score - exact score| (f32 bits)
 };
+// One thread per raw log entry of a debug_raw_scores run: accumulates max |gemm - f64 dot(q16,x)| (tensor-core accumulation),
+// max |sequential f32 - f64 dot(q,x)| (the re-score's own rounding), max |gemm - sequential f32| / eps_q, a histogram of
+// |gemm - sequential f32| by binary exponent, and the pair count.  out: 8 doubles-as-u64 maxima/ratios + 40 bins + count.
+cudaError_t launch_score_error(const uint2 *log, const uint32_t *cnt, int n_queries, int log_cap, const __half *corpus,
+                               const float *q32, const __half *q16, const float *eps_q, unsigned long long *out,
+                               cudaStream_t s);
 // K5+K6: merge per-CTA lists, re-score candidates in the reference's order of summation
 // (src/search/vector.rs:128-134), final order and 1 - score.
 cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s);
@@ -199,6 +206,12 @@ struct GemmSearch {
     const float **eps_out;    // out: device pointer to per-query eps
     const uint32_t **overflow_out;  // out: device pointer to per-query overflow flags
     int *launches_out;        // out: kernels launched
+    // debug (dawn_debug_gemm_score_error): run ONE round over all tiles with thresholds at -inf, skip the select, and hand back
+    // the raw logs -- every (query,row) score the tensor cores produced.  Needs n_rows <= 2048 (the log capacity).
+    int debug_raw_scores;
+    const uint2 **debug_log_out;     // [qp][2048] (score bits, row)
+    const uint32_t **debug_cnt_out;  // [qp]
+    const __half **debug_q16_out;    // [qp][384] the fp16-rounded queries the MMA used
 };
 // K3: tcgen05 GEMM + fused top-k' over geometrically growing rounds of rows (gemm_topk.cu).
 cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s);

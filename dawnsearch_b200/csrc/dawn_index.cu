@@ -1609,6 +1609,75 @@ int dawn_index_load(dawn_index *idx, const char *path) {
     return DAWN_OK;
 }
 
+// ---- evidence for the certificate's constants (tests/test_gpu_slack.py) -----------------------------------
+// Every (query,row) score the tensor cores produce for `batch` host queries against an index of <= 2048 rows is compared
+// on the device with (a) the f64 dot product of the SAME fp16 operands (pure accumulation error of the MMA), (b) the
+// sequential f32 re-score (what the exact answer is made of) and (c) the f64 dot product of the f32 query (the re-score's own
+// rounding).  Results accumulate across calls in *acc (zero it first).
+int dawn_debug_gemm_score_error(dawn_index *idx, const float *queries, size_t batch, dawn_score_error *acc) {
+    int rc = check_alive(idx);
+    if (rc) return rc;
+    if (!queries || !acc || batch == 0) return fail(DAWN_ERR_INVALID, "null argument");
+    if (idx->scalar != DAWN_SCALAR_F16) return fail(DAWN_ERR_INVALID, "fp16 storage only");
+    std::shared_lock<std::shared_mutex> rd;
+    size_t n = 0;
+    float eps_scale = 1.0f;
+    rc = snapshot_for_search(idx, rd, &n, &eps_scale);
+    if (rc) return rc;
+    if (n == 0 || n > 2048) return fail(DAWN_ERR_INVALID, "the index must hold 1..2048 rows (one candidate log per query)");
+    WsLease lease(idx);
+    SearchWs *ws = lease.ws;
+    if (!ws) return fail(DAWN_ERR_CUDA, "cannot create a search workspace");
+    rc = ensure_query_ws(idx, ws, batch, 1);
+    if (rc) return rc;
+    if ((rc = ensure_gemm_ws(idx, ws, gemm_workspace_bytes((int)batch)))) return rc;
+    cudaStream_t s = ws->stream;
+    memcpy(ws->h_queries, queries, batch * kDim * sizeof(float));
+    CK(idx, cudaMemcpyAsync(ws->d_queries, ws->h_queries, batch * kDim * sizeof(float), cudaMemcpyHostToDevice, s));
+    GemmSearch gs{};
+    gs.corpus = idx->corpus;
+    gs.labels = idx->labels;
+    gs.n_rows = n;
+    gs.queries = ws->d_queries;
+    gs.n_queries = (int)batch;
+    gs.kprime = 16;
+    fill_gemm_knobs(idx, gs);
+    gs.workspace = ws->d_gemm_ws;
+    gs.final_lists = nullptr;
+    gs.accum_slack = kGemmAccumSlack;
+    gs.limit_score = -INFINITY;
+    gs.debug_raw_scores = 1;
+    const float *eps_q = nullptr;
+    const uint2 *log = nullptr;
+    const uint32_t *cnt = nullptr;
+    const __half *q16 = nullptr;
+    gs.eps_out = &eps_q;
+    gs.debug_log_out = &log;
+    gs.debug_cnt_out = &cnt;
+    gs.debug_q16_out = &q16;
+    CK(idx, launch_gemm_search(gs, s));
+    unsigned long long *d_out = nullptr;
+    CK(idx, cudaMalloc(&d_out, 48 * sizeof(unsigned long long)));
+    CK(idx, cudaMemsetAsync(d_out, 0, 48 * sizeof(unsigned long long), s));
+    CK(idx, launch_score_error(log, cnt, (int)batch, 2048, idx->corpus, ws->d_queries, q16, eps_q, d_out, s));
+    unsigned long long h[48];
+    CK(idx, cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, s));
+    CK(idx, cudaStreamSynchronize(s));
+    cudaFree(d_out);
+    auto as_double = [](unsigned long long u) { double d; memcpy(&d, &u, 8); return d; };
+    auto upd = [](double &a, double b) { if (b > a) a = b; };
+    upd(acc->max_mma_vs_f64, as_double(h[0]));
+    upd(acc->max_seq_vs_f64, as_double(h[1]));
+    upd(acc->max_mma_vs_seq, as_double(h[2]));
+    upd(acc->max_err_over_eps_q, as_double(h[3]));
+    acc->pairs += h[4];
+    for (int b = 0; b < 40; b++) acc->hist[b] += h[8 + b];
+    acc->scan_eps = kScanEps;
+    acc->gemm_accum_slack = kGemmAccumSlack;
+    acc->i8_dequant_slack = kI8DequantSlack;
+    return DAWN_OK;
+}
+
 int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value) {
     int rc = check_alive(idx);
     if (rc) return rc;
@@ -1660,6 +1729,11 @@ int dawn_index_get_profile(dawn_index *idx, dawn_profile *out, int reset) {
     *out = idx->prof;
     out->device_uncertified = idx->h_stats[0];
     out->device_status = idx->h_stats[1];
+    {
+        float e;
+        memcpy(&e, &idx->h_stats[2], 4);
+        out->max_selection_error = e;
+    }
     if (reset) idx->prof = dawn_profile{};
     return DAWN_OK;
 }

@@ -398,7 +398,10 @@ int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, s
         g_multi_err = "exchange = nccl requested but no communicator exists (one shard, or a device listed twice)";
         return DAWN_ERR_INVALID;
     }
-    const bool use_nccl = m->nccl_ready && m->exchange != 1;
+    // auto: the all-gather for real batches; for a handful of queries the blocks are a few hundred bytes and one peer copy per
+    // shard into the first device is ~60 us quicker than eight communicators' worth of collective launches (measured on
+    // 8 B200: 18 us against 84 us for exchange + merge at batch 1, profiles/r02_front_multi_k10_8gpu.json)
+    const bool use_nccl = m->nccl_ready && (m->exchange == 2 || (m->exchange == 0 && bb > 16384));
     Shard *s0 = m->shards[0];
     cudaError_t e = cudaSetDevice(s0->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");

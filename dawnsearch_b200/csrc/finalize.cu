@@ -294,6 +294,12 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
                 }
                 acc = __fmul_rn(*reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(corpus) + i8_scale_offset(mine.row)), acc);
             }
+            // evidence for the certificate's eps: the largest |selection score - exact score| ever seen (tests/test_gpu_slack.py)
+            if (stats) {
+                const float err = fabsf(my_scan - acc);
+                if (err == err && __float_as_uint(err) > *reinterpret_cast<volatile uint32_t *>(&stats[2]))
+                    atomicMax(&stats[2], __float_as_uint(err));
+            }
             mine.score = __fsub_rn(1.0f, acc);  // distance, vector.rs:133
         }
     }
@@ -363,6 +369,76 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
 }
 
 }  // namespace
+
+namespace {
+// see launch_score_error in dawn_common.cuh
+__global__ void __launch_bounds__(256) score_error_kernel(const uint2 *__restrict__ log, const uint32_t *__restrict__ cnt,
+                                                          int n_queries, int log_cap, const __half *__restrict__ corpus,
+                                                          const float *__restrict__ q32, const __half *__restrict__ q16,
+                                                          const float *__restrict__ eps_q, unsigned long long *__restrict__ out) {
+    const int q = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double d_acc = 0.0, d_seq = 0.0, d_tot = 0.0, ratio = 0.0;
+    bool have = false;
+    if (q < n_queries && i < (int)min(cnt[q], (uint32_t)log_cap)) {
+        const uint2 e = log[(size_t)q * log_cap + i];
+        const float gemm = __uint_as_float(e.x);
+        const __half *x = corpus + (size_t)e.y * kDim;
+        const float *qf = q32 + (size_t)q * kDim;
+        const __half *qh = q16 + (size_t)q * kDim;
+        double dot16 = 0.0, dot32 = 0.0;
+        float seq = 0.0f;
+        for (int c = 0; c < kDim; c++) {
+            const float xv = __half2float(x[c]);
+            dot16 += (double)__half2float(qh[c]) * (double)xv;
+            dot32 += (double)qf[c] * (double)xv;
+            seq = __fadd_rn(seq, __fmul_rn(qf[c], xv));
+        }
+        d_acc = fabs((double)gemm - dot16);
+        d_seq = fabs((double)seq - dot32);
+        d_tot = fabs((double)gemm - (double)seq);
+        ratio = d_tot / (double)eps_q[q];
+        have = true;
+        int ex;
+        frexp(d_tot, &ex);  // d_tot in [2^(ex-1), 2^ex)
+        int bin = d_tot == 0.0 ? 0 : ex + 39;  // bin b >= 1: [2^(b-40), 2^(b-39))
+        bin = bin < 1 ? (d_tot == 0.0 ? 0 : 1) : (bin > 39 ? 39 : bin);
+        atomicAdd(&out[8 + bin], 1ull);
+    }
+    // block maxima (doubles are non-negative: their bit patterns order like the values)
+    __shared__ unsigned long long red[4][8];
+    unsigned long long v[4] = {(unsigned long long)__double_as_longlong(d_acc), (unsigned long long)__double_as_longlong(d_seq),
+                               (unsigned long long)__double_as_longlong(d_tot), (unsigned long long)__double_as_longlong(ratio)};
+    const unsigned ballot = __ballot_sync(0xffffffffu, have);
+    for (int k = 0; k < 4; k++) {
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[k], off);
+            v[k] = o > v[k] ? o : v[k];
+        }
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v[k];
+    }
+    __shared__ unsigned int s_pairs;
+    if (threadIdx.x == 0) s_pairs = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_pairs, __popc(ballot));
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        unsigned long long m = 0;
+        for (int w = 0; w < 8; w++) m = red[threadIdx.x][w] > m ? red[threadIdx.x][w] : m;
+        atomicMax(&out[threadIdx.x], m);
+    }
+    if (threadIdx.x == 0) atomicAdd(&out[4], (unsigned long long)s_pairs);
+}
+}  // namespace
+
+cudaError_t launch_score_error(const uint2 *log, const uint32_t *cnt, int n_queries, int log_cap, const __half *corpus,
+                               const float *q32, const __half *q16, const float *eps_q, unsigned long long *out,
+                               cudaStream_t s) {
+    if (n_queries <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((log_cap + 255) / 256), (unsigned)n_queries);
+    score_error_kernel<<<grid, 256, 0, s>>>(log, cnt, n_queries, log_cap, corpus, q32, q16, eps_q, out);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s) {
     if (p.nq == 0) return cudaSuccess;

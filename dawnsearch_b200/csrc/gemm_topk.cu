@@ -571,6 +571,10 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
     mult %= total_tiles > 0 ? total_tiles : 1;
     if (mult == 0) mult = 1;
     uint64_t begin = 0, end = 1024 / BN;  // in (permuted) tiles: round 0 = 4 tiles = 1024 rows
+    if (p.debug_raw_scores) {
+        if (p.n_rows > (uint64_t)kSelCap) return cudaErrorInvalidValue;
+        end = total_tiles;  // one round, thresholds still at -inf: every valid (query,row) score lands in the log
+    }
     while (begin < total_tiles) {
         if (end > total_tiles || end + end / 4 > total_tiles) end = total_tiles;  // fold a short last round into this one
         const uint64_t n_tiles = end - begin;
@@ -587,6 +591,13 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
             e = launch_gemm_round<1>(p.grid, s, tmap_q, tmap_x, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows,
                                      (uint32_t)total_tiles, (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow);
         if (e != cudaSuccess) return e;
+        if (p.debug_raw_scores) {
+            if (p.debug_log_out) *p.debug_log_out = log;
+            if (p.debug_cnt_out) *p.debug_cnt_out = cnt;
+            if (p.debug_q16_out) *p.debug_q16_out = q16;
+            launches += 1;
+            break;
+        }
         const bool last = end >= total_tiles;
         select_topk_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, thr, overflow, kSelCap, p.kprime, p.labels,
                                                       last ? p.final_lists : nullptr, eps_q, p.limit_score);

@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(128) prep_queries_i8_kernel(const float *__res
         out[qi].s2 = s2;
         // |sum e_i x_i| <= ||e|| * ||x||; dequantised rows have norm < 1.02; + f32 rounding of the
         // three-operation score formula
-        eps_q[qi] = sqrtf(red[0] + red[1] + red[2] + red[3]) * 1.03f + 2.0e-5f;
+        eps_q[qi] = sqrtf(red[0] + red[1] + red[2] + red[3]) * 1.03f + 3.0e-5f;  // 384 * 2^-24 * 1.03 = 2.4e-5 for the sequential re-score alone
     }
 }
 

@@ -73,10 +73,31 @@ class Profile(C.Structure):
         ("gemm_ms", C.c_double),
         ("device_uncertified", C.c_uint64),
         ("device_status", C.c_uint64),
+        ("max_selection_error", C.c_double),
     ]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class ScoreError(C.Structure):
+    _fields_ = [
+        ("max_mma_vs_f64", C.c_double),
+        ("max_seq_vs_f64", C.c_double),
+        ("max_mma_vs_seq", C.c_double),
+        ("max_err_over_eps_q", C.c_double),
+        ("pairs", C.c_uint64),
+        ("hist", C.c_uint64 * 40),
+        ("scan_eps", C.c_float),
+        ("gemm_accum_slack", C.c_float),
+        ("i8_dequant_slack", C.c_float),
+        ("reserved_", C.c_float),
+    ]
+
+    def as_dict(self):
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n not in ("hist", "reserved_")}
+        d["hist"] = list(self.hist)
+        return d
 
 
 class MultiStats(C.Structure):
@@ -154,6 +175,7 @@ def load_library() -> C.CDLL:
     L.dawn_index_set_profiling.argtypes = [_vp, C.c_int]
     L.dawn_index_set_option.argtypes = [_vp, C.c_char_p, C.c_int64]
     L.dawn_index_get_profile.argtypes = [_vp, C.POINTER(Profile), C.c_int]
+    L.dawn_debug_gemm_score_error.argtypes = [_vp, _vp, C.c_size_t, C.POINTER(ScoreError)]
     L.dawn_vector_length.argtypes = [_vp]
     L.dawn_vector_length.restype = C.c_float
     L.dawn_is_normalized.argtypes = [_vp]
@@ -357,6 +379,11 @@ class Index:
         """Raw device-pointer entry point (ints are CUDA device addresses); only enqueues."""
         _check(self._L.dawn_index_search_device(self._h, d_queries, batch, count, d_labels, d_dist,
                                                 d_counts, d_flags, stream))
+
+    def debug_gemm_score_error(self, queries, acc: "ScoreError") -> None:
+        """Accumulate tensor-core score errors over every (query,row) pair (index of <= 2048 rows); see dawn_index.h."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, EM_LEN)
+        _check(self._L.dawn_debug_gemm_score_error(self._h, _ptr(q), q.shape[0], C.byref(acc)))
 
     def set_option(self, key: str, value: int) -> None:
         """'gemm_min_batch', 'gemm_min_rows', 'force_path' (0 auto, 1 scan, 2 tensor-core)."""

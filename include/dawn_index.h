@@ -214,7 +214,8 @@ size_t dawn_multi_size(const dawn_multi *m);
 size_t dawn_multi_capacity(const dawn_multi *m);
 size_t dawn_multi_shards(const dawn_multi *m);
 const char *dawn_multi_last_error(void);
-/* "exchange": 0 = auto (NCCL all-gather; peer copies when a device is listed twice or there is one shard),
+/* "exchange": 0 = auto (NCCL all-gather; peer copies when a device is listed twice, there is one shard, or the result
+ * blocks are under 16 KB -- a handful of queries, where one small peer copy per shard is quicker than a collective),
  * 1 = peer copies (cudaMemcpyPeerAsync into the first device), 2 = NCCL or fail.  Any other key is passed
  * to every shard's dawn_index_set_option. */
 int dawn_multi_set_option(dawn_multi *m, const char *key, int64_t value);
@@ -245,6 +246,9 @@ typedef struct dawn_profile {
      * every scan status word (nonzero = internal buffer overflow, a bug). */
     uint64_t device_uncertified;
     uint64_t device_status;
+    /* Largest |selection score - exact re-score| over every candidate any finalize launch has handled since the last reset
+     * (all paths).  The certificate's eps constants must stay above it: tests/test_gpu_slack.py. */
+    double max_selection_error;
 } dawn_profile;
 /* enable != 0: record CUDA events around every K2 / finalize launch (adds host syncs when
  * read).  Off by default. */
@@ -258,6 +262,21 @@ int dawn_index_set_profiling(dawn_index *idx, int enable);
  * "gemm_cta_group", "gemm_chunk_tiles", "gemm_growth", "gemm_sequential_tiles": A/B knobs of the tensor-core path, 0 = automatic. */
 int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value);
 int dawn_index_get_profile(dawn_index *idx, dawn_profile *out, int reset);
+
+/* Evidence for the exactness certificate's constants (not a search path).  For `batch` host queries against an fp16 index of
+ * at most 2048 rows, EVERY (query,row) score the tensor-core kernel produces is compared on the device with the f64 dot
+ * product of the same fp16 operands, with the sequential f32 re-score and with the f64 dot product of the f32 query.
+ * Maxima, pair count and a histogram of |tensor-core score - sequential score| accumulate in *acc across calls. */
+typedef struct dawn_score_error {
+    double max_mma_vs_f64;       /* |tcgen05 score - f64 dot(fp16(q), x)|: the MMA's own accumulation error */
+    double max_seq_vs_f64;       /* |sequential f32 score - f64 dot(q, x)|: rounding of the exact re-score */
+    double max_mma_vs_seq;       /* |tcgen05 score - sequential f32 score|: what eps_q has to bound */
+    double max_err_over_eps_q;   /* max of that difference divided by the query's eps_q (must stay below 1) */
+    uint64_t pairs;
+    uint64_t hist[40];           /* hist[0]: difference == 0; hist[b]: difference in [2^(b-40), 2^(b-39)) */
+    float scan_eps, gemm_accum_slack, i8_dequant_slack, reserved_;  /* the constants compiled into the library */
+} dawn_score_error;
+int dawn_debug_gemm_score_error(dawn_index *idx, const float *queries, size_t batch, dawn_score_error *acc);
 
 #ifdef __cplusplus
 }
