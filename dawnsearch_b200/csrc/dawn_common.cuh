@@ -84,6 +84,8 @@ cudaError_t launch_ingest_f16(const float *src_f32, __half *dst, size_t n_rows, 
 // Synthetic rows [first_row, first_row+n) written straight into the corpus arena.
 cudaError_t launch_synth_f16(__half *dst, uint64_t seed, uint64_t first_row, size_t n_rows,
                              cudaStream_t s);
+// the same rows before the fp16 rounding (DAWN_SCALAR_F32 storage); bit-identical to oracle/dawn_oracle.c:dawn_oracle_synth_row_f32
+cudaError_t launch_synth_f32(float *dst, uint64_t seed, uint64_t first_row, size_t n_rows, cudaStream_t s);
 // Gather stored rows back to f32 (dawn_index_get; SearchProvider::embedding_for_page,
 // src/search/search_provider.rs:183-195, served from the device corpus).
 cudaError_t launch_gather_f32(const __half *corpus, const uint32_t *rows, size_t n, float *out,
@@ -122,7 +124,9 @@ struct FinalizeLaunch {
     float *distances_out;   // [nq][k]
     uint32_t *counts_out;   // [nq]
     uint32_t *flags_out;    // [nq] bit0 = exactness certified
-    int scalar;             // 0 = fp16 rows (corpus is __half*), 1 = blocked int8 arena (corpus is uint8_t*)
+    int scalar;             // 0 = fp16 rows (corpus is __half*), 1 = blocked int8 arena (corpus is uint8_t*),
+                            // 2 = re-score from corpus32 (the f32 vectors as given); selection ran on the fp16 copies
+    const float *corpus32;  // scalar == 2 only
     const float *eps_q;     // optional per-query eps (GEMM path: depends on the query's fp16 rounding)
     const uint32_t *overflow;  // optional per-query "candidate log overflowed" flags -> not certified
     uint32_t *counters;     // optional: [n_counters] words (status word first) that CTA 0 zeroes for the next search

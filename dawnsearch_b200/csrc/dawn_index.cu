@@ -54,6 +54,7 @@ constexpr size_t kStageRowsHost = 8192;  // pinned staging: 8192 vectors = 12 MB
 // observed maximum at least twofold; the histogram is committed under profiles/.
 constexpr float kScanEps = 3.0e-5f;         // K2: two f32 summation orders over 384 terms, |q||x| <= 1.03
 constexpr float kGemmAccumSlack = 6.0e-5f;  // K3: tensor-core f32 accumulation over K=384 + the sequential re-score
+constexpr float kF32StoreSlack = 5.1e-4f;   // DAWN_SCALAR_F32: selection runs on fp16 copies, |q.(fp16(x) - x)| <= 2^-11 |q||x| = 4.9e-4 * 1.01^2
 constexpr float kRowNormGate = 1.0105f;     // the reference's gate (vector.rs:185-192) plus fp16 / int8 rounding
 constexpr int kMaxPoolWs = 8;               // host searches in flight per handle
 constexpr size_t kBulkMinRows = 32768;      // add_batch calls at least this large take the parallel bulk pipeline
@@ -129,6 +130,7 @@ struct dawn_index {
 
     int scalar = DAWN_SCALAR_F16;  // storage of the corpus: fp16 rows or the blocked int8 arena
     __half *corpus = nullptr;      // fp16: [phys][384]; int8: the same pointer holds the blocked arena
+    float *corpus32 = nullptr;     // DAWN_SCALAR_F32 only: the vectors as given, [phys][384] f32 (what the exact re-score reads)
     uint64_t *labels = nullptr;
     std::atomic<size_t> size{0};      // rows committed to the device
     std::atomic<size_t> capacity{0};  // logical capacity promised to the caller
@@ -345,12 +347,24 @@ void wait_device_searches(dawn_index *idx) {
     if (idx->dev_ws && idx->dev_ws->ws_used) cudaEventSynchronize(idx->dev_ws->ws_done);
 }
 
-int alloc_arena(dawn_index *idx, size_t rows, __half **corpus_out, uint64_t **labels_out) {
+int alloc_arena(dawn_index *idx, size_t rows, __half **corpus_out, uint64_t **labels_out, float **corpus32_out) {
     __half *nc = nullptr;
     uint64_t *nl = nullptr;
+    *corpus32_out = nullptr;
+    if (idx->scalar == DAWN_SCALAR_F32) {
+        cudaError_t e32 = cudaMalloc(corpus32_out, rows * (size_t)kDim * sizeof(float));
+        if (e32 != cudaSuccess) {
+            cudaGetLastError();
+            *corpus32_out = nullptr;
+            return fail(DAWN_ERR_CAPACITY, "cannot allocate %zu bytes of HBM for %zu f32 vectors: %s", rows * (size_t)kDim * 4, rows,
+                        cudaGetErrorString(e32));
+        }
+    }
     cudaError_t e = cudaMalloc(&nc, arena_bytes(idx, rows));
     if (e != cudaSuccess) {
         cudaGetLastError();
+        cudaFree(*corpus32_out);
+        *corpus32_out = nullptr;
         return fail(DAWN_ERR_CAPACITY, "cannot allocate %zu bytes of HBM for %zu vectors: %s", arena_bytes(idx, rows), rows,
                     cudaGetErrorString(e));
     }
@@ -358,6 +372,8 @@ int alloc_arena(dawn_index *idx, size_t rows, __half **corpus_out, uint64_t **la
     if (e != cudaSuccess) {
         cudaGetLastError();
         cudaFree(nc);
+        cudaFree(*corpus32_out);
+        *corpus32_out = nullptr;
         return fail(DAWN_ERR_CAPACITY, "cannot allocate label table for %zu vectors", rows);
     }
     *corpus_out = nc;
@@ -377,31 +393,37 @@ int grow_physical(dawn_index *idx, size_t rows) {
     }
     __half *nc = nullptr;
     uint64_t *nl = nullptr;
-    int rc = alloc_arena(idx, want, &nc, &nl);
+    float *n32 = nullptr;
+    int rc = alloc_arena(idx, want, &nc, &nl, &n32);
     if (rc != DAWN_OK && want > rows) {
         want = rows;
-        rc = alloc_arena(idx, want, &nc, &nl);
+        rc = alloc_arena(idx, want, &nc, &nl, &n32);
     }
     if (rc != DAWN_OK) return rc;
     const size_t n = idx->size;
     if (n > 0) {
+        if (n32) CK(idx, cudaMemcpyAsync(n32, idx->corpus32, n * (size_t)kDim * sizeof(float), cudaMemcpyDeviceToDevice, idx->stream));
         CK(idx, cudaMemcpyAsync(nc, idx->corpus, arena_bytes(idx, n), cudaMemcpyDeviceToDevice, idx->stream));
         CK(idx, cudaMemcpyAsync(nl, idx->labels, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, idx->stream));
         CK(idx, cudaStreamSynchronize(idx->stream));
     }
     __half *oc;
     uint64_t *ol;
+    float *o32;
     {
         std::unique_lock<std::shared_mutex> wr(idx->corpus_mu);
         wait_device_searches(idx);
         oc = idx->corpus;
         ol = idx->labels;
+        o32 = idx->corpus32;
         idx->corpus = nc;
         idx->labels = nl;
+        idx->corpus32 = n32;
         idx->phys = want;
     }
     if (oc) cudaFree(oc);
     if (ol) cudaFree(ol);
+    if (o32) cudaFree(o32);
     return DAWN_OK;
 }
 
@@ -415,6 +437,8 @@ int flush_staged_async(dawn_index *idx) {
     CK(idx, cudaMemcpyAsync(idx->d_stage, idx->h_stage, n * kDim * sizeof(float), cudaMemcpyHostToDevice, idx->stream));
     if (idx->scalar == DAWN_SCALAR_I8) CK(idx, launch_ingest_i8(idx->d_stage, arena_i8(idx), at, n, idx->stream));
     else CK(idx, launch_ingest_f16(idx->d_stage, idx->corpus + at * kDim, n, idx->stream));
+    if (idx->corpus32)  // the vectors as given, for the exact f32 re-score
+        CK(idx, cudaMemcpyAsync(idx->corpus32 + at * kDim, idx->d_stage, n * kDim * sizeof(float), cudaMemcpyDeviceToDevice, idx->stream));
     CK(idx, cudaMemcpyAsync(idx->labels + at, idx->h_stage_labels, n * sizeof(uint64_t), cudaMemcpyHostToDevice, idx->stream));
     CK(idx, cudaEventRecord(idx->stage_done[cur], idx->stream));
     idx->stage_busy[cur] = true;
@@ -453,7 +477,7 @@ int flush_staged(dawn_index *idx) {
 int ensure_norms_checked(dawn_index *idx) {
     const size_t n = idx->size;
     if (idx->norm_checked >= n) return DAWN_OK;
-    CK(idx, launch_verify_rows(idx->corpus, idx->scalar, idx->norm_checked, n - idx->norm_checked, idx->d_norm_stats, idx->stream));
+    CK(idx, launch_verify_rows(idx->corpus, idx->scalar == DAWN_SCALAR_I8 ? 1 : 0, idx->norm_checked, n - idx->norm_checked, idx->d_norm_stats, idx->stream));
     CK(idx, cudaMemcpyAsync(idx->h_norm_stats, idx->d_norm_stats, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, idx->stream));
     CK(idx, cudaStreamSynchronize(idx->stream));
     idx->bad_rows = idx->h_norm_stats[0];
@@ -780,6 +804,11 @@ int search_enqueue(dawn_index *idx, SearchWs *ws, const float *d_queries, size_t
     int rc;
     // a pushed-down limit is only sound with the nominal eps values
     const float limit_score = ws->eps_scale == 1.0f ? ws->limit_score : -INFINITY;
+    // DAWN_SCALAR_F32: candidates are selected on the fp16 copies and re-scored on the f32 vectors as given; the copies'
+    // rounding (<= kF32StoreSlack in score) joins every eps, and the lists are at least 64 deep so the certificate has room
+    const bool f32_store = idx->scalar == DAWN_SCALAR_F32;
+    const float store_slack = f32_store ? kF32StoreSlack : 0.0f;
+    if (f32_store && kprime < 64) kprime = 64;
     if (idx->scalar == DAWN_SCALAR_I8 && !scan_only && idx->i8_tensor_min_batch > 0 &&
         (int64_t)batch >= idx->i8_tensor_min_batch && n >= 65536 && idx->i8_native)
         return search_i8_native(idx, ws, d_queries, batch, k, kprime, d_labels_out, d_dist_out, d_counts, d_flags, s, d_status_out);
@@ -863,8 +892,8 @@ int search_enqueue(dawn_index *idx, SearchWs *ws, const float *d_queries, size_t
         fill_gemm_knobs(idx, gs);
         gs.workspace = ws->d_gemm_ws;
         gs.final_lists = ws->d_partials;
-        gs.accum_slack = kGemmAccumSlack;
-        gs.limit_score = limit_score;
+        gs.accum_slack = kGemmAccumSlack + store_slack;
+        gs.limit_score = limit_score > -INFINITY ? limit_score - store_slack : limit_score;
         const float *eps_q = nullptr;
         const uint32_t *overflow = nullptr;
         int launches = 0;
@@ -890,7 +919,8 @@ int search_enqueue(dawn_index *idx, SearchWs *ws, const float *d_queries, size_t
         fl.distances_out = d_dist_out;
         fl.counts_out = d_counts;
         fl.flags_out = d_flags;
-        fl.scalar = 0;
+        fl.scalar = f32_store ? 2 : 0;
+        fl.corpus32 = idx->corpus32;
         fl.eps_q = eps_q;
         fl.overflow = overflow;
         fl.counters = ws->d_counters;
@@ -919,7 +949,7 @@ int search_enqueue(dawn_index *idx, SearchWs *ws, const float *d_queries, size_t
         sl.chunk_counter = ws->d_counters + 1 + pass;
         sl.status = ws->d_counters;
         sl.grid = grid;
-        sl.score_floor = limit_score > -INFINITY ? limit_score - 2.0f * kScanEps - 1e-6f : -INFINITY;
+        sl.score_floor = limit_score > -INFINITY ? limit_score - 2.0f * (kScanEps + store_slack) - 1e-6f : -INFINITY;
         EventPair ev;
         bool timed = begin_event(idx, ws, 0, s, &ev);
         CK(idx, launch_scan_topk_f16(sl, s));
@@ -938,12 +968,13 @@ int search_enqueue(dawn_index *idx, SearchWs *ws, const float *d_queries, size_t
     fl.n_lists = grid;
     fl.kprime = kprime;
     fl.k = (int)k;
-    fl.eps = kScanEps;
+    fl.eps = kScanEps + store_slack;
     fl.labels_out = d_labels_out;
     fl.distances_out = d_dist_out;
     fl.counts_out = d_counts;
     fl.flags_out = d_flags;
-    fl.scalar = 0;
+    fl.scalar = f32_store ? 2 : 0;
+    fl.corpus32 = idx->corpus32;
     fl.eps_q = nullptr;
     fl.overflow = nullptr;
     fl.counters = ws->d_counters;
@@ -1112,6 +1143,8 @@ int bulk_add(dawn_index *idx, const uint64_t *labels, const float *vectors, size
             if (e == cudaSuccess)
                 e = idx->scalar == DAWN_SCALAR_I8 ? launch_ingest_i8(L.d_buf[turn], arena_i8(idx), at + r0, cnt, L.stream)
                                                   : launch_ingest_f16(L.d_buf[turn], idx->corpus + (at + r0) * kDim, cnt, L.stream);
+            if (e == cudaSuccess && idx->corpus32)
+                e = cudaMemcpyAsync(idx->corpus32 + (at + r0) * kDim, L.d_buf[turn], cnt * kDim * sizeof(float), cudaMemcpyDeviceToDevice, L.stream);
             if (e == cudaSuccess)
                 e = cudaMemcpyAsync(idx->labels + at + r0, L.h_lab[turn], cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, L.stream);
             if (e == cudaSuccess) e = cudaEventRecord(L.done[turn], L.stream);
@@ -1156,8 +1189,8 @@ int dawn_index_create(const dawn_options *opts, dawn_index **out) {
         return fail(DAWN_ERR_INVALID, "dimensions must be %d (src/search/vector.rs:26), got %u",
                     DAWN_DIMENSIONS, o.dimensions);
     if (o.metric != DAWN_METRIC_IP) return fail(DAWN_ERR_INVALID, "only MetricKind::IP is supported");
-    if (o.scalar != DAWN_SCALAR_F16 && o.scalar != DAWN_SCALAR_I8)
-        return fail(DAWN_ERR_INVALID, "scalar must be DAWN_SCALAR_F16 or DAWN_SCALAR_I8, got %u", o.scalar);
+    if (o.scalar != DAWN_SCALAR_F16 && o.scalar != DAWN_SCALAR_I8 && o.scalar != DAWN_SCALAR_F32)
+        return fail(DAWN_ERR_INVALID, "scalar must be DAWN_SCALAR_F16, DAWN_SCALAR_I8 or DAWN_SCALAR_F32, got %u", o.scalar);
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0) {
@@ -1228,6 +1261,7 @@ void dawn_index_free(dawn_index *idx) {
     free_ws(idx->dev_ws);
     if (idx->bulk_ready) bulk_teardown(idx);
     cudaFree(idx->corpus);
+    cudaFree(idx->corpus32);
     cudaFree(idx->labels);
     for (int b = 0; b < 2; b++) {
         cudaFree(idx->d_stage_buf[b]);
@@ -1302,7 +1336,10 @@ int dawn_index_add_synthetic(dawn_index *idx, uint64_t seed, uint64_t first_row,
         return fail(DAWN_ERR_CAPACITY, "add of %zu vectors exceeds capacity %zu (size %zu): reserve first", n,
                     idx->capacity.load(), at);
     if (idx->scalar == DAWN_SCALAR_I8) CK(idx, launch_synth_i8(arena_i8(idx), at, seed, first_row, n, idx->stream));
-    else CK(idx, launch_synth_f16(idx->corpus + at * kDim, seed, first_row, n, idx->stream));
+    else if (idx->scalar == DAWN_SCALAR_F32) {
+        CK(idx, launch_synth_f32(idx->corpus32 + at * kDim, seed, first_row, n, idx->stream));
+        CK(idx, launch_ingest_f16(idx->corpus32 + at * kDim, idx->corpus + at * kDim, n, idx->stream));
+    } else CK(idx, launch_synth_f16(idx->corpus + at * kDim, seed, first_row, n, idx->stream));
     CK(idx, launch_iota_labels(idx->labels + at, first_row + 1, n, idx->stream));  // labels = first_row + i + 1
     CK(idx, cudaStreamSynchronize(idx->stream));
     idx->size = at + n;
@@ -1414,6 +1451,8 @@ int dawn_index_get(dawn_index *idx, uint64_t label, float *vector384_out) {
     CK(idx, cudaStreamSynchronize(s));
     if (h_row[0] == kNoRow) return fail(DAWN_ERR_INVALID, "label %llu not found", (unsigned long long)label);
     if (idx->scalar == DAWN_SCALAR_I8) CK(idx, launch_gather_f32_i8(arena_i8(idx), d_row, 1, ws->d_queries, s));
+    else if (idx->scalar == DAWN_SCALAR_F32)  // the vector exactly as it was added
+        CK(idx, cudaMemcpyAsync(ws->d_queries, idx->corpus32 + (size_t)h_row[0] * kDim, kDim * sizeof(float), cudaMemcpyDeviceToDevice, s));
     else CK(idx, launch_gather_f32(idx->corpus, d_row, 1, ws->d_queries, s));
     ws->prof.kernel_launches++;
     CK(idx, cudaMemcpyAsync(ws->h_queries, ws->d_queries, kDim * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -1499,7 +1538,8 @@ int dawn_index_save(dawn_index *idx, const char *path) {
         return DAWN_OK;
     };
     rc = dump(idx->labels, n * sizeof(uint64_t));
-    if (rc == DAWN_OK) rc = dump(idx->corpus, arena_bytes(idx, n));
+    if (rc == DAWN_OK)  // F32 storage persists the vectors as given; the fp16 selection copy is rebuilt on load
+        rc = idx->scalar == DAWN_SCALAR_F32 ? dump(idx->corpus32, n * (size_t)kDim * sizeof(float)) : dump(idx->corpus, arena_bytes(idx, n));
     ok = (fclose(f) == 0) && ok;
     if (rc != DAWN_OK || !ok) {
         remove(tmp.c_str());
@@ -1532,7 +1572,8 @@ int dawn_index_load(dawn_index *idx, const char *path) {
     }
     fseek(f, 0, SEEK_END);
     long long flen = ftell(f);
-    long long want = (long long)sizeof h + (long long)h.size * 8 + (long long)arena_bytes(idx, h.size);
+    const size_t payload = idx->scalar == DAWN_SCALAR_F32 ? (size_t)h.size * kDim * sizeof(float) : arena_bytes(idx, h.size);
+    long long want = (long long)sizeof h + (long long)h.size * 8 + (long long)payload;
     if (flen != want) {
         fclose(f);
         return fail(DAWN_ERR_IO, "%s is truncated (%lld bytes, expected %lld)", path, flen, want);
@@ -1545,8 +1586,9 @@ int dawn_index_load(dawn_index *idx, const char *path) {
     const size_t rows_alloc = h.size > idx->capacity ? (size_t)h.size : idx->capacity.load();
     __half *nc = nullptr;
     uint64_t *nl = nullptr;
+    float *n32 = nullptr;
     if (rows_alloc > 0) {
-        rc = alloc_arena(idx, rows_alloc, &nc, &nl);
+        rc = alloc_arena(idx, rows_alloc, &nc, &nl, &n32);
         if (rc) {
             fclose(f);
             return rc;
@@ -1576,7 +1618,12 @@ int dawn_index_load(dawn_index *idx, const char *path) {
         }
     };
     slurp(nl, h.size * sizeof(uint64_t));
-    slurp(nc, arena_bytes(idx, h.size));
+    if (idx->scalar == DAWN_SCALAR_F32) {
+        slurp(n32, payload);
+        if (ok && ce == cudaSuccess && h.size) ce = launch_ingest_f16(n32, nc, (size_t)h.size, idx->stream);  // rebuild the selection copy
+    } else {
+        slurp(nc, payload);
+    }
     fclose(f);
     cudaError_t se = cudaStreamSynchronize(idx->stream);
     idx->stage_busy[0] = idx->stage_busy[1] = false;
@@ -1584,6 +1631,7 @@ int dawn_index_load(dawn_index *idx, const char *path) {
     if (!ok || ce != cudaSuccess) {
         cudaFree(nc);
         cudaFree(nl);
+        cudaFree(n32);
         if (ce != cudaSuccess) {
             cudaGetLastError();
             return fail(DAWN_ERR_IO, "copy to the device failed while loading %s: %s (index unchanged)", path, cudaGetErrorString(ce));
@@ -1592,19 +1640,23 @@ int dawn_index_load(dawn_index *idx, const char *path) {
     }
     __half *oc;
     uint64_t *ol;
+    float *o32;
     {
         std::unique_lock<std::shared_mutex> wr(idx->corpus_mu);
         wait_device_searches(idx);
         oc = idx->corpus;
         ol = idx->labels;
+        o32 = idx->corpus32;
         idx->corpus = nc;
         idx->labels = nl;
+        idx->corpus32 = n32;
         idx->phys = rows_alloc;
         idx->size = (size_t)h.size;
         if (idx->capacity < (size_t)h.size) idx->capacity = (size_t)h.size;
     }
     cudaFree(oc);
     cudaFree(ol);
+    cudaFree(o32);
     reset_norm_stats(idx);
     return DAWN_OK;
 }
@@ -1618,7 +1670,7 @@ int dawn_debug_gemm_score_error(dawn_index *idx, const float *queries, size_t ba
     int rc = check_alive(idx);
     if (rc) return rc;
     if (!queries || !acc || batch == 0) return fail(DAWN_ERR_INVALID, "null argument");
-    if (idx->scalar != DAWN_SCALAR_F16) return fail(DAWN_ERR_INVALID, "fp16 storage only");
+    if (idx->scalar == DAWN_SCALAR_I8) return fail(DAWN_ERR_INVALID, "fp16 / f32 storage only");
     std::shared_lock<std::shared_mutex> rd;
     size_t n = 0;
     float eps_scale = 1.0f;

@@ -205,7 +205,7 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
                 uint32_t *__restrict__ counts_out, uint32_t *__restrict__ flags_out,
                 const float *__restrict__ eps_q, const uint32_t *__restrict__ overflow, int scalar,
                 uint32_t *__restrict__ counters, int n_counters, uint32_t *__restrict__ status_out, float eps_scale,
-                uint32_t *__restrict__ stats) {
+                uint32_t *__restrict__ stats, const float *__restrict__ corpus32) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FinSmem &sm = *reinterpret_cast<FinSmem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -243,7 +243,7 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
     // ---- K6: exact re-score.  The survivors' rows are first staged in shared memory by the whole CTA
     // (coalesced, one round trip to L2/HBM), then one thread per candidate adds the 384 products
     // sequentially in f32 -- the reference's order (vector.rs:128-134).
-    const bool stage_rows = n_lists > 1;
+    const bool stage_rows = n_lists > 1 && scalar != 2;  // f32 rows (1536 B each) are read in place
     const int entries = n_lists == 1 ? kp : kFinCapEntries;
     uint8_t *rows_sm = reinterpret_cast<uint8_t *>(sm.s + entries);
     const int stride = scalar ? kRowStrideI8 : kRowStrideF16;
@@ -271,7 +271,19 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
                                   : reinterpret_cast<const uint4 *>(
                                         scalar ? reinterpret_cast<const uint8_t *>(corpus) + i8_row_offset(mine.row)
                                                : reinterpret_cast<const uint8_t *>(corpus + (size_t)mine.row * kDim));
-            if (scalar == 0) {
+            if (scalar == 2) {
+                // DAWN_SCALAR_F32: the exact score is over the f32 vector as it was added -- what the reference's
+                // ScalarKind::F32 index stores (search_provider.rs:38) -- in the reference's order (vector.rs:128-134)
+                const float4 *xp = reinterpret_cast<const float4 *>(corpus32 + (size_t)mine.row * kDim);
+#pragma unroll 4
+                for (int c = 0; c < kDim / 4; c++) {
+                    const float4 x = __ldg(xp + c);
+                    acc = __fadd_rn(acc, __fmul_rn(sm.q[4 * c], x.x));
+                    acc = __fadd_rn(acc, __fmul_rn(sm.q[4 * c + 1], x.y));
+                    acc = __fadd_rn(acc, __fmul_rn(sm.q[4 * c + 2], x.z));
+                    acc = __fadd_rn(acc, __fmul_rn(sm.q[4 * c + 3], x.w));
+                }
+            } else if (scalar == 0) {
 #pragma unroll 4
                 for (int c = 0; c < kDim / 8; c++) {
                     const uint4 u = rp[c];
@@ -446,7 +458,9 @@ cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s) {
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const size_t smem = fin_smem_bytes(p.n_lists == 1 ? p.kprime : kFinCapEntries, p.kprime, p.scalar, p.n_lists > 1);
+    if (p.scalar == 2 && !p.corpus32) return cudaErrorInvalidValue;
+    const size_t smem = fin_smem_bytes(p.n_lists == 1 ? p.kprime : kFinCapEntries, p.kprime, p.scalar == 1 ? 1 : 0,
+                                       p.n_lists > 1 && p.scalar != 2);
     if (dev < 64 && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)fin_smem_bytes(kFinCapEntries, kMaxCand, 0, true));
@@ -456,7 +470,7 @@ cudaError_t launch_finalize(const FinalizeLaunch &p, cudaStream_t s) {
     finalize_kernel<<<p.nq, p.n_lists == 1 ? kFinThreadsSingle : kFinThreads, smem, s>>>(
         p.corpus, p.queries, p.partials, p.n_lists, p.kprime, p.k, p.eps, p.labels_out, p.distances_out, p.counts_out,
         p.flags_out, p.eps_q, p.overflow, p.scalar, p.counters, p.n_counters, p.status_out,
-        p.eps_scale > 0.f ? p.eps_scale : 1.0f, p.stats);
+        p.eps_scale > 0.f ? p.eps_scale : 1.0f, p.stats, p.corpus32);
     return cudaGetLastError();
 }
 

@@ -64,6 +64,39 @@ __global__ void __launch_bounds__(256) synth_f16_kernel(__half *__restrict__ dst
     }
 }
 
+// The synthetic rows as f32 (one warp per row, same column split as synth_f16_kernel).
+__global__ void __launch_bounds__(256) synth_f32_kernel(float *__restrict__ dst, uint64_t seed, uint64_t first_row,
+                                                        size_t n_rows) {
+    const int lane = threadIdx.x & 31;
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t r = warp; r < n_rows; r += n_warps) {
+        uint64_t row = first_row + r;
+        int32_t raw[12];
+        long long sumsq = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) raw[j] = synth_raw(seed, row, lane * 8 + j);
+#pragma unroll
+        for (int j = 0; j < 4; j++) raw[8 + j] = synth_raw(seed, row, 256 + lane * 4 + j);
+#pragma unroll
+        for (int j = 0; j < 12; j++) sumsq += (long long)raw[j] * raw[j];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sumsq += __shfl_xor_sync(0xffffffffu, sumsq, off);
+        if (sumsq == 0) {
+            if (lane == 0) raw[0] = 1;
+            sumsq = 1;
+        }
+        double inv = 1.0 / sqrt((double)sumsq);
+        float x[12];
+#pragma unroll
+        for (int j = 0; j < 12; j++) x[j] = (float)((double)raw[j] * inv);
+        float *out = dst + r * kDim;
+        *reinterpret_cast<float4 *>(out + lane * 8) = make_float4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<float4 *>(out + lane * 8 + 4) = make_float4(x[4], x[5], x[6], x[7]);
+        *reinterpret_cast<float4 *>(out + 256 + lane * 4) = make_float4(x[8], x[9], x[10], x[11]);
+    }
+}
+
 __global__ void __launch_bounds__(128) gather_f32_kernel(const __half *__restrict__ corpus,
                                                          const uint32_t *__restrict__ rows, size_t n,
                                                          float *__restrict__ out) {
@@ -195,6 +228,14 @@ cudaError_t launch_synth_f16(__half *dst, uint64_t seed, uint64_t first_row, siz
     size_t blocks = (n_rows + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
     synth_f16_kernel<<<(unsigned)blocks, 256, 0, s>>>(dst, seed, first_row, n_rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_synth_f32(float *dst, uint64_t seed, uint64_t first_row, size_t n_rows, cudaStream_t s) {
+    if (n_rows == 0) return cudaSuccess;
+    size_t blocks = (n_rows + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    synth_f32_kernel<<<(unsigned)blocks, 256, 0, s>>>(dst, seed, first_row, n_rows);
     return cudaGetLastError();
 }
 

@@ -45,6 +45,7 @@ class MetricKind:  # usearch::ffi::MetricKind (search_provider.rs:37)
 class ScalarKind:  # usearch::ffi::ScalarKind (search_provider.rs:38); storage precision
     F16 = 0
     I8 = 1
+    F32 = 2  # the reference's own setting: f32 vectors kept as given, exact f32 distances
 
 
 class _Options(C.Structure):
@@ -229,8 +230,8 @@ class Index:
 
     def __init__(self, options: IndexOptions):
         L = load_library()
-        if options.quantization not in (ScalarKind.F16, ScalarKind.I8):
-            raise DawnError(-1, "quantization must be ScalarKind.F16 or ScalarKind.I8")
+        if options.quantization not in (ScalarKind.F16, ScalarKind.I8, ScalarKind.F32):
+            raise DawnError(-1, "quantization must be ScalarKind.F16, ScalarKind.I8 or ScalarKind.F32")
         o = _Options(options.dimensions, options.metric, options.quantization, options.device,
                      options.capacity, 0, 0)
         h = _vp()

@@ -61,14 +61,20 @@ enum {
 };
 
 /* usearch ScalarKind equivalents for the stored corpus (search_provider.rs:38). */
-enum { DAWN_SCALAR_F16 = 0, DAWN_SCALAR_I8 = 1 };
+enum {
+    DAWN_SCALAR_F16 = 0, /* fp16 rows, 768 B per vector: "exact" = exact over the fp16-rounded vectors */
+    DAWN_SCALAR_I8 = 1,  /* int8 + per-vector f32 scale, 388 B per vector */
+    DAWN_SCALAR_F32 = 2  /* the reference's own ScalarKind::F32 (search_provider.rs:38): the f32 vectors are kept as given
+                          * (1536 B) beside an fp16 selection copy (768 B); distances are those of an exact f32 brute force
+                          * over the vectors as added, bit for bit */
+};
 /* usearch MetricKind::IP (search_provider.rs:37) is the only metric the reference uses. */
 enum { DAWN_METRIC_IP = 0 };
 
 typedef struct dawn_options {
     uint32_t dimensions; /* must be 384 (0 = default) */
     uint32_t metric;     /* DAWN_METRIC_IP */
-    uint32_t scalar;     /* DAWN_SCALAR_F16, or DAWN_SCALAR_I8 (per-vector absmax/127 scale, 388 B per vector) */
+    uint32_t scalar;     /* DAWN_SCALAR_F16, DAWN_SCALAR_I8 (per-vector absmax/127 scale) or DAWN_SCALAR_F32 */
     int32_t device;      /* CUDA device ordinal */
     uint64_t capacity;   /* vectors to reserve up front (0 = none) */
     uint32_t flags;      /* reserved, 0 */
