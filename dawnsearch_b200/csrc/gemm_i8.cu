@@ -24,7 +24,7 @@
 // Shape of one CTA (384 threads, 1 CTA/SM, persistent over work units):
 //   A operand  = one 128-query tile of hi (int8), K-major, resident in shared memory: 3 k-blocks of 128 rows x 128 B  48 KB
 //   B operand  = corpus tiles of 256 rows = 32 arena blocks, streamed k-block by k-block (256 x 128 B = 32 KB per stage)
-//                by a 3-D TMA tensor map over the blocked arena {384 B row, 8 rows per block, blocks of 3104 B}    96 KB ring
+//                by a 3-D TMA tensor map over the blocked arena {384 B row, 8 rows per block, blocks of 3104 B}   128 KB ring
 //   scales     = the tile's 256 per-row f32 scales (they sit behind each block's rows), their own 2-D TMA map      8 x 1 KB ring
 //   D          = 128 x 256 s32 in TMEM, two buffers; 12 MMAs (K = 32) per tile
 //   warp 0 TMA producer, warp 1 MMA issuer + TMEM alloc, warps 4-11 epilogue: two warps per TMEM lane quarter, each
@@ -49,8 +49,10 @@ constexpr int BN = 256;             // corpus rows per tile (UMMA N) = 32 arena 
 constexpr int BKB = 128;            // int8 elements (= bytes) per k-block = one swizzle-atom row
 constexpr int kKBlocks = kDim / BKB;  // 3
 constexpr int kUmmaKBytes = 32;     // one kind::i8 MMA covers K = 32
-constexpr int kMaxStagesB = 6;      // 3 x 32 KB (one CTA) or 6 x 16 KB (CTA pair)
-constexpr int kBRingBytes = 3 * BN * BKB;      // 98304 either way
+constexpr int kRingTiles32K = 4;    // B ring depth in 32 KB units: one int8 tile lasts ~1 us, about a DRAM round trip, so the ring
+                                    // holds 1 1/3 tiles (the fp16 kernel's 3 stages hold half of its 2 us tile)
+constexpr int kMaxStagesB = 2 * kRingTiles32K;  // 4 x 32 KB (one CTA) or 8 x 16 KB (CTA pair)
+constexpr int kBRingBytes = kRingTiles32K * BN * BKB;  // 131072 either way
 constexpr int kABlockBytes = BM * BKB;         // 16384
 constexpr int kABytes = kABlockBytes * kKBlocks;  // 49152
 constexpr int kTmemCols = 512;
@@ -58,7 +60,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kStageCap = 16;       // survivors an epilogue thread parks in shared memory before one atomic flush
 constexpr int kStagingBytes = kStageCap * kEpiThreads * 8;  // 32 KB
-constexpr int kScaleSlots = 8;      // scale tiles in flight; the producer runs at most 4 tiles ahead of the epilogue
+constexpr int kScaleSlots = 8;      // scale tiles in flight; the producer runs at most 5 tiles ahead of the epilogue
 constexpr int kScaleTileBytes = BN * 4;
 constexpr int kBarBytes = 512;
 constexpr int kGroupMaxBytes = kEpiWarps * 32 * 4;  // per epilogue warp: the largest scale of each group of 4 columns
@@ -98,7 +100,7 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     uint32_t n_tiles_total, uint32_t perm_mult, int n_qtiles, int n_queries, int chunk_tiles,
                     const float *__restrict__ thr_g, uint32_t *__restrict__ cnt_g, uint2 *__restrict__ log_g,
                     uint32_t *__restrict__ overflow_g, int log_cap) {
-    constexpr int kStagesB = 3 * CG;
+    constexpr int kStagesB = kRingTiles32K * CG;
     constexpr int kBRows = BN / CG;                  // corpus rows this CTA streams per tile
     constexpr int kBStageBytes = kBRows * BKB;       // 32 KB or 16 KB
     constexpr uint32_t kIdesc = make_idesc_i8(BM * CG);

@@ -11,7 +11,8 @@ k = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 knob = sys.argv[4] if len(sys.argv) > 4 else "gemm_sequential_tiles"
 values = [int(v) for v in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0, 1]
 settings = [{knob: v} for v in values]
-idx = D.new_index(D.IndexOptions(capacity=rows))
+scalar = os.environ.get("DAWN_AB_SCALAR", "f16")
+idx = D.new_index(D.IndexOptions(capacity=rows, quantization=D.ScalarKind.I8 if scalar == "i8" else D.ScalarKind.F16))
 idx.add_synthetic(0xDA5EA2C4, 0, rows)
 dev = torch.device("cuda:0")
 q = torch.from_numpy(synth.make_queries(0xDA5EA2C4, 3, batch, rows)).to(dev)
