@@ -71,19 +71,24 @@ try:
     import torch
     if torch.cuda.is_available():
         import dawnsearch_b200 as D
-        with D.new_index(D.IndexOptions(capacity=n)) as idx:
-            idx.add_batch(labels, rows)
-            for _ in range(5):
-                idx.search(qs[0], 10)
-            lat, same = [], 0
-            want = O.cpu_scan_f16(stored16, labels, qs, 10)
-            for i, q in enumerate(qs):
-                t1 = time.perf_counter()
-                m = idx.search(q, 10)
-                lat.append((time.perf_counter() - t1) * 1e6)
-                same += int((m.labels == want[0][i]).all() and (m.distances.view(np.uint32) == want[1][i].view(np.uint32)).all())
-            out["b200_exact_c_abi"] = {"p50_us": round(statistics.median(lat), 1), "p99_us": round(sorted(lat)[int(0.99 * len(lat))], 1),
-                                       "bit_identical_to_oracle": f"{same}/{nq}", "recall": 1.0}
+        out["b200_exact_c_abi"] = {}
+        for name, quant in (("f32_storage", D.ScalarKind.F32), ("fp16_storage", D.ScalarKind.F16)):
+            with D.new_index(D.IndexOptions(capacity=n, quantization=quant)) as idx:
+                idx.add_batch(labels, rows)
+                for _ in range(5):
+                    idx.search(qs[0], 10)
+                lat, same = [], 0
+                if quant == D.ScalarKind.F32:   # C1 as stated: f32 page vectors -> exact f32 brute force is the truth
+                    want = ([O.search_f32(rows, labels, q, 10)[0] for q in qs], [O.search_f32(rows, labels, q, 10)[1] for q in qs])
+                else:
+                    want = O.cpu_scan_f16(stored16, labels, qs, 10)
+                for i, q in enumerate(qs):
+                    t1 = time.perf_counter()
+                    m = idx.search(q, 10)
+                    lat.append((time.perf_counter() - t1) * 1e6)
+                    same += int((m.labels == want[0][i]).all() and (m.distances.view(np.uint32) == want[1][i].view(np.uint32)).all())
+                out["b200_exact_c_abi"][name] = {"p50_us": round(statistics.median(lat), 1), "p99_us": round(sorted(lat)[int(0.99 * len(lat))], 1),
+                                                 "bit_identical_to_oracle": f"{same}/{nq}", "recall": 1.0}
 except Exception as e:  # no GPU here: CPU part only
     out["b200_exact_c_abi"] = f"unavailable: {e}"
 print(json.dumps(out))

@@ -11,6 +11,9 @@ k = int(sys.argv[4]) if len(sys.argv) > 4 else 10
 quant = D.ScalarKind.I8 if kind.startswith("i8") else D.ScalarKind.F16
 with D.new_index(D.IndexOptions(capacity=rows, quantization=quant)) as idx:
     idx.add_synthetic(0xDA5EA2C4, 0, rows)
+    for kv in filter(None, os.environ.get("DAWN_OPTS", "").split(",")):  # e.g. DAWN_OPTS=gemm_chunk_tiles=8,gemm_cta_group=1
+        key, val = kv.split("=")
+        idx.set_option(key, int(val))
     qs = synth.make_queries(0xDA5EA2C4, 4, batch, rows, planted_fraction=0.25)
     for _ in range(2):
         r = idx.search_batch(qs, k)
