@@ -260,6 +260,7 @@ int dawn_multi_create(const int *devices, size_t n_devices, uint32_t scalar, daw
 
 void dawn_multi_free(dawn_multi *m) {
     if (!m) return;
+    const int dev0 = m->shards.empty() ? -1 : m->shards[0]->device;  // the shards are deleted below
     for (Shard *s : m->shards) {
         if (s->th.joinable()) {
             {
@@ -284,7 +285,7 @@ void dawn_multi_free(dawn_multi *m) {
         dawn_index_free(s->idx);
         delete s;
     }
-    if (!m->shards.empty()) cudaSetDevice(m->shards[0]->device);
+    if (dev0 >= 0) cudaSetDevice(dev0);
     if (m->ev_x0) cudaEventDestroy(m->ev_x0);
     if (m->ev_x1) cudaEventDestroy(m->ev_x1);
     cudaFree(m->d_gather);
