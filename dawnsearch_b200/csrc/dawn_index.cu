@@ -166,7 +166,8 @@ struct dawn_index {
     // path selection: batches >= gemm_min_batch over >= gemm_min_rows rows take the tensor-core path
     std::atomic<int64_t> gemm_min_batch{16};
     std::atomic<int64_t> gemm_min_rows{65536};
-    std::atomic<int64_t> gemm_small_batch{3};  // from this batch size on, big corpora also take the tensor path
+    std::atomic<int64_t> gemm_small_batch{2};  // from this batch size on, big corpora also take the tensor path (r02 C4 sweeps: batch 2
+                                               // costs 6.35 ms as a QT=2 scan and 5.7 ms on the tensor path at 50M rows)
     std::atomic<int64_t> gemm_small_batch_rows{2000000};
     std::atomic<int64_t> force_path{0};  // 0 auto, 1 scan only, 2 gemm whenever possible
     std::atomic<int64_t> gemm_cta_group{0};  // 0 auto, 1 = one CTA per tile, 2 = CTA pairs
@@ -809,8 +810,9 @@ int search_enqueue(dawn_index *idx, SearchWs *ws, const float *d_queries, size_t
     const bool f32_store = idx->scalar == DAWN_SCALAR_F32;
     const float store_slack = f32_store ? kF32StoreSlack : 0.0f;
     if (f32_store && kprime < 64) kprime = 64;
+    const bool i8_small_on_big = (int64_t)batch >= idx->gemm_small_batch && (int64_t)n >= idx->gemm_small_batch_rows;
     if (idx->scalar == DAWN_SCALAR_I8 && !scan_only && idx->i8_tensor_min_batch > 0 &&
-        (int64_t)batch >= idx->i8_tensor_min_batch && n >= 65536 && idx->i8_native)
+        ((int64_t)batch >= idx->i8_tensor_min_batch || i8_small_on_big) && n >= 65536 && idx->i8_native)
         return search_i8_native(idx, ws, d_queries, batch, k, kprime, d_labels_out, d_dist_out, d_counts, d_flags, s, d_status_out);
     if (idx->scalar == DAWN_SCALAR_I8 && !scan_only && idx->i8_tensor_min_batch > 0 &&
         (int64_t)batch >= idx->i8_tensor_min_batch && n >= 65536 && k <= 100)

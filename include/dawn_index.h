@@ -262,7 +262,7 @@ int dawn_index_set_profiling(dawn_index *idx, int enable);
 /* Tuning knobs: "gemm_min_batch" (default 16) and "gemm_min_rows" (default 65536) decide when a
  * batch takes the tensor-core path instead of repeated streaming scans; "force_path" 0 = auto,
  * 1 = scan only, 2 = tensor-core path whenever the corpus holds >= 1024 vectors.
- * "gemm_small_batch" (3) / "gemm_small_batch_rows" (2M): on big corpora even small batches take the tensor-core path.
+ * "gemm_small_batch" (2) / "gemm_small_batch_rows" (2M): on big corpora even small batches take the tensor-core path (fp16 and int8).
  * int8 corpora: "i8_tensor_min_batch" (16, 0 = never) -- from this batch size on the corpus is dequantised chunk by chunk
  * ("i8_tensor_chunk_rows", 4M) into an fp16 scratch and searched on the tensor cores; results stay bit-identical.
  * "gemm_cta_group", "gemm_chunk_tiles", "gemm_growth", "gemm_sequential_tiles": A/B knobs of the tensor-core path, 0 = automatic. */
