@@ -203,6 +203,7 @@ struct GemmSearch {
     int chunk_tiles;          // 0 = auto; tiles per work unit (tuning override)
     int sequential_tiles;     // 1 = visit tiles in stored order instead of the strided permutation (A/B only)
     int growth;               // rows visited grow by this factor per round (0 = automatic: 8, or up to 32 for one query tile)
+    int no_unit_sync;         // 1 = no rendezvous of the workers that share a corpus chunk (A/B only)
     void *workspace;          // gemm_workspace_bytes(n_queries)
     Cand *final_lists;        // out: [ceil128(n_queries)][kprime] sorted candidates (approximate scores)
     float accum_slack;        // bound on the tensor-core accumulation error added to every eps_q
@@ -235,6 +236,7 @@ struct GemmSearchI8 {
     int chunk_tiles;          // 0 = auto
     int sequential_tiles;     // 1 = visit tiles in stored order (A/B only)
     int growth;               // 0 = automatic
+    int no_unit_sync;         // 1 = no rendezvous of the workers that share a corpus chunk (A/B only)
     void *workspace;          // gemm_i8_workspace_bytes(n_queries)
     Cand *final_lists;        // out: [ceil256(n_queries)][kprime] candidates with EXACT scores (unsorted)
     float limit_score;        // 1 - distance_limit (-inf = none)

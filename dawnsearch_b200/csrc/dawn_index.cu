@@ -174,6 +174,7 @@ struct dawn_index {
     std::atomic<int64_t> gemm_chunk_tiles{0};
     std::atomic<int64_t> gemm_sequential_tiles{0};
     std::atomic<int64_t> gemm_growth{0};
+    std::atomic<int64_t> gemm_unit_sync{1};  // rendezvous of the workers sharing a corpus chunk (gemm_pipe.cuh)
     // int8 corpora: batches of at least this many queries take the tensor cores.  0 = never.
     std::atomic<int64_t> i8_tensor_min_batch{16};
     std::atomic<int64_t> i8_tensor_chunk_rows{4 << 20};
@@ -633,6 +634,7 @@ void fill_gemm_knobs(const dawn_index *idx, GemmSearch &gs) {
     gs.chunk_tiles = (int)idx->gemm_chunk_tiles;
     gs.sequential_tiles = (int)idx->gemm_sequential_tiles;
     gs.growth = (int)idx->gemm_growth;
+    gs.no_unit_sync = idx->gemm_unit_sync ? 0 : 1;
 }
 
 int run_finalize(dawn_index *idx, SearchWs *ws, FinalizeLaunch &fl, cudaStream_t s, size_t batch) {
@@ -759,6 +761,7 @@ int search_i8_native(dawn_index *idx, SearchWs *ws, const float *d_queries, size
     gs.chunk_tiles = (int)idx->gemm_chunk_tiles;
     gs.sequential_tiles = (int)idx->gemm_sequential_tiles;
     gs.growth = (int)idx->gemm_growth;
+    gs.no_unit_sync = idx->gemm_unit_sync ? 0 : 1;
     gs.workspace = ws->d_gemm_ws;
     gs.final_lists = ws->d_partials;
     gs.limit_score = ws->eps_scale == 1.0f ? ws->limit_score : -INFINITY;
@@ -1745,6 +1748,7 @@ int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value) {
     else if (!strcmp(key, "gemm_chunk_tiles")) idx->gemm_chunk_tiles = value;
     else if (!strcmp(key, "gemm_sequential_tiles")) idx->gemm_sequential_tiles = value;
     else if (!strcmp(key, "gemm_growth")) idx->gemm_growth = value;
+    else if (!strcmp(key, "gemm_unit_sync")) idx->gemm_unit_sync = value;
     else if (!strcmp(key, "i8_tensor_min_batch")) idx->i8_tensor_min_batch = value;
     else if (!strcmp(key, "i8_tensor_chunk_rows")) idx->i8_tensor_chunk_rows = value < 65536 ? 65536 : value;
     else if (!strcmp(key, "i8_native")) idx->i8_native = value;

@@ -103,7 +103,7 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     const __grid_constant__ CUtensorMap tmap_s, uint32_t tile_begin, uint32_t tile_end, uint32_t n_rows,
                     uint32_t n_tiles_total, uint32_t perm_mult, int n_qtiles, int n_queries, int chunk_tiles,
                     const float *__restrict__ thr_g, uint32_t *__restrict__ cnt_g, uint2 *__restrict__ log_g,
-                    uint32_t *__restrict__ overflow_g, int log_cap) {
+                    uint32_t *__restrict__ overflow_g, int log_cap, uint32_t *__restrict__ chunk_arrive) {
     constexpr int kStagesB = kRingTiles32K * CG;
     constexpr int kBRows = BN / CG;                  // corpus rows this CTA streams per tile
     constexpr int kBStageBytes = kBRows * BKB;       // 32 KB or 16 KB
@@ -195,6 +195,8 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 cur_t = t;
                 n_reload++;
             }
+            if (chunk_arrive != nullptr && chunk < (uint32_t)kArriveSlots)  // start the chunk together with its other query tiles
+                chunk_rendezvous(chunk_arrive + chunk, (uint32_t)n_qtiles, cta_rank == 0);
             const uint32_t tile0 = chunk * chunk_tiles;
             const uint32_t tile1 = min(n_tiles, tile0 + chunk_tiles);
             uint32_t pt = phys_tile(tile0);
@@ -462,8 +464,9 @@ __global__ void __launch_bounds__(kSelThreads) select_i8_kernel(uint2 *__restric
                                                                 const float *__restrict__ s1_g, const float *__restrict__ e1_g,
                                                                 float limit_score, float eps_scale,
                                                                 const uint64_t *__restrict__ labels,
-                                                                Cand *__restrict__ final_lists) {
+                                                                Cand *__restrict__ final_lists, uint32_t *__restrict__ arrive) {
     __shared__ unsigned long long keys[kSelCap];
+    clear_arrive_slots(arrive, blockIdx.x, gridDim.x, threadIdx.x, kSelThreads);
     __shared__ unsigned long long s_prefix;
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_need, s_out;
@@ -579,7 +582,7 @@ template <int CG>
 cudaError_t launch_round(int grid, cudaStream_t s, const CUtensorMap &tq, const CUtensorMap &tx, const CUtensorMap &ts,
                          uint32_t tile_begin, uint32_t tile_end, uint32_t n_rows, uint32_t n_tiles_total, uint32_t perm_mult,
                          int n_qtiles, int n_queries, int chunk, const float *thr, uint32_t *cnt, uint2 *log,
-                         uint32_t *overflow) {
+                         uint32_t *overflow, uint32_t *arrive) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kI8Threads);
@@ -594,14 +597,14 @@ cudaError_t launch_round(int grid, cudaStream_t s, const CUtensorMap &tq, const 
     cfg.numAttrs = 1;
     int log_cap = kSelCap;
     return cudaLaunchKernelEx(&cfg, gemm_i8_topk_kernel<CG>, tq, tx, ts, tile_begin, tile_end, n_rows, n_tiles_total, perm_mult,
-                              n_qtiles, n_queries, chunk, thr, cnt, log, overflow, log_cap);
+                              n_qtiles, n_queries, chunk, thr, cnt, log, overflow, log_cap, arrive);
 }
 
 }  // namespace
 
 size_t gemm_i8_workspace_bytes(int n_queries) {
     const size_t qp = ((size_t)n_queries + 2 * BM - 1) / (2 * BM) * (2 * BM);
-    return qp * kDim + qp * (6 * sizeof(float)) + qp * (size_t)kSelCap * sizeof(uint2) + 1024;
+    return qp * kDim + qp * (6 * sizeof(float)) + qp * (size_t)kSelCap * sizeof(uint2) + 1024 + kArriveSlots * sizeof(uint32_t);
 }
 
 cudaError_t launch_gemm_search_i8(const GemmSearchI8 &p, cudaStream_t s) {
@@ -630,6 +633,7 @@ cudaError_t launch_gemm_search_i8(const GemmSearchI8 &p, cudaStream_t s) {
     w += (size_t)qp * sizeof(uint32_t);
     w = reinterpret_cast<uint8_t *>(((uintptr_t)w + 255) & ~(uintptr_t)255);
     uint2 *log = reinterpret_cast<uint2 *>(w);
+    uint32_t *arrive = (n_qtiles > 1 && !p.no_unit_sync) ? reinterpret_cast<uint32_t *>(w + (size_t)qp * kSelCap * sizeof(uint2)) : nullptr;
 
     static bool configured[64] = {};
     int dev = 0;
@@ -652,7 +656,7 @@ cudaError_t launch_gemm_search_i8(const GemmSearchI8 &p, cudaStream_t s) {
     prep_queries_i8_gemm_kernel<<<qp, 128, 0, s>>>(p.queries, p.n_queries, q8, s1, e1);
     // thresholds before the first round: -inf, or the pushed-down limit (a select pass over empty logs)
     select_i8_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, kept, thr, overflow, kSelCap, p.kprime, p.arena, p.queries,
-                                                p.n_queries, s1, e1, p.limit_score, p.eps_scale, p.labels, nullptr);
+                                                p.n_queries, s1, e1, p.limit_score, p.eps_scale, p.labels, nullptr, arrive);
     int launches = 2;
     // Rounds grow x8 (x4 for k' = 128): the filter band e1 lets ~2x more rows through than an exact threshold would,
     // (growth - 1) * k' * 2.2 + k' entries must fit the 2048-entry log with margin.
@@ -672,22 +676,19 @@ cudaError_t launch_gemm_search_i8(const GemmSearchI8 &p, cudaStream_t s) {
         const uint64_t n_tiles = end - begin;
         uint64_t chunk = (n_tiles * (uint64_t)n_qtiles + (uint64_t)workers * 4 - 1) / ((uint64_t)workers * 4);
         if (chunk < 1) chunk = 1;
-        // 16 tiles (1.6 MB of corpus) per unit: the CTA pairs that share a chunk start it at slightly different times, and the
-        // rows have to survive in L2 for that long; with 64-tile units ncu read 1.48x the algorithmic bytes from DRAM, with 8-tile
-        // units 1.05x but 8 % more cycles (a query-tile reload per unit).  profiles/r02_i8_dram_traffic_vs_chunk.txt
-        if (chunk > 16) chunk = 16;
+        if (chunk > 64) chunk = 64;
         if (p.chunk_tiles > 0) chunk = (uint64_t)p.chunk_tiles;
         if (cg == 2)
             e = launch_round<2>(p.grid, s, tq, tx, ts, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows, (uint32_t)total_tiles,
-                                (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow);
+                                (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow, arrive);
         else
             e = launch_round<1>(p.grid, s, tq, tx, ts, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows, (uint32_t)total_tiles,
-                                (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow);
+                                (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow, arrive);
         if (e != cudaSuccess) return e;
         const bool last = end >= total_tiles;
         select_i8_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, kept, thr, overflow, kSelCap, p.kprime, p.arena, p.queries,
                                                     p.n_queries, s1, e1, p.limit_score, p.eps_scale, p.labels,
-                                                    last ? p.final_lists : nullptr);
+                                                    last ? p.final_lists : nullptr, arrive);
         launches += 2;
         begin = end;
         end = end * growth;

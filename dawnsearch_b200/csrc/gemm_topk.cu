@@ -89,7 +89,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                  uint32_t tile_begin, uint32_t tile_end, uint32_t n_rows, uint32_t n_tiles_total, uint32_t perm_mult,
                  int n_qtiles, int n_queries,
                  int chunk_tiles, const float *__restrict__ thr_g, uint32_t *__restrict__ cnt_g,
-                 uint2 *__restrict__ log_g, uint32_t *__restrict__ overflow_g, int log_cap) {
+                 uint2 *__restrict__ log_g, uint32_t *__restrict__ overflow_g, int log_cap, uint32_t *__restrict__ chunk_arrive) {
     constexpr int kStagesB = 3 * CG;
     constexpr int kBRows = BN / CG;                 // corpus rows this CTA streams per tile
     constexpr int kBStageBytes = kBRows * BK * 2;   // 32 KB or 16 KB
@@ -188,6 +188,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 cur_t = t;
                 n_reload++;
             }
+            if (chunk_arrive != nullptr && chunk < (uint32_t)kArriveSlots)  // start the chunk together with its other query tiles
+                chunk_rendezvous(chunk_arrive + chunk, (uint32_t)n_qtiles, cta_rank == 0);
             const uint32_t tile0 = chunk * chunk_tiles;
             const uint32_t tile1 = min(n_tiles, tile0 + chunk_tiles);
             uint32_t pt = phys_tile(tile0);
@@ -398,8 +400,10 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(uint2 *__restr
                                                                   uint32_t *__restrict__ overflow_g, int log_cap, int kp,
                                                                   const uint64_t *__restrict__ labels,
                                                                   Cand *__restrict__ final_lists,
-                                                                  const float *__restrict__ eps_q, float limit_score) {
+                                                                  const float *__restrict__ eps_q, float limit_score,
+                                                                  uint32_t *__restrict__ arrive) {
     __shared__ unsigned long long keys[kSelCap];
+    clear_arrive_slots(arrive, blockIdx.x, gridDim.x, threadIdx.x, kSelThreads);
     __shared__ unsigned long long s_prefix;
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_need, s_out;
@@ -473,14 +477,15 @@ bool make_tmap(CUtensorMap *map, const void *base, uint64_t rows, uint32_t box_r
 
 size_t gemm_workspace_bytes(int n_queries) {
     const size_t qp = ((size_t)n_queries + 2 * BM - 1) / (2 * BM) * (2 * BM);  // pair mode pads to 256
-    return qp * kDim * sizeof(__half) + qp * (4 * sizeof(float)) + qp * (size_t)kSelCap * sizeof(uint2) + 1024;
+    return qp * kDim * sizeof(__half) + qp * (4 * sizeof(float)) + qp * (size_t)kSelCap * sizeof(uint2) + 1024 +
+           kArriveSlots * sizeof(uint32_t);
 }
 
 template <int CG>
 static cudaError_t launch_gemm_round(int grid, cudaStream_t s, const CUtensorMap &tmap_q, const CUtensorMap &tmap_x,
                                      uint32_t tile_begin, uint32_t tile_end, uint32_t n_rows, uint32_t n_tiles_total,
                                      uint32_t perm_mult, int n_qtiles, int n_queries, int chunk, const float *thr,
-                                     uint32_t *cnt, uint2 *log, uint32_t *overflow) {
+                                     uint32_t *cnt, uint2 *log, uint32_t *overflow, uint32_t *arrive) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kGemmThreads);
@@ -495,7 +500,7 @@ static cudaError_t launch_gemm_round(int grid, cudaStream_t s, const CUtensorMap
     cfg.numAttrs = 1;
     int log_cap = kSelCap;
     return cudaLaunchKernelEx(&cfg, gemm_topk_kernel<CG>, tmap_q, tmap_x, tile_begin, tile_end, n_rows, n_tiles_total,
-                              perm_mult, n_qtiles, n_queries, chunk, thr, cnt, log, overflow, log_cap);
+                              perm_mult, n_qtiles, n_queries, chunk, thr, cnt, log, overflow, log_cap, arrive);
 }
 
 cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
@@ -522,6 +527,8 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
     w += (size_t)qp * sizeof(uint32_t);
     w = reinterpret_cast<uint8_t *>(((uintptr_t)w + 255) & ~(uintptr_t)255);
     uint2 *log = reinterpret_cast<uint2 *>(w);
+    // chunk rendezvous counters (gemm_pipe.cuh): only when several query tiles share the corpus; "gemm_unit_sync" = 0 turns it off
+    uint32_t *arrive = (n_qtiles > 1 && !p.no_unit_sync) ? reinterpret_cast<uint32_t *>(w + (size_t)qp * kSelCap * sizeof(uint2)) : nullptr;
 
     static bool configured[64] = {};
     int dev = 0;
@@ -544,7 +551,7 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
     {
         // -inf thresholds: written by a select pass over empty logs (cnt == 0 -> thr = -inf)
         select_topk_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, thr, overflow, kSelCap, p.kprime, p.labels, nullptr, eps_q,
-                                                      p.limit_score);
+                                                      p.limit_score, arrive);
     }
     int launches = 2;
     // rounds of rows: [0,1024), then x`growth` each time ((growth-1)*k' survivors per query per
@@ -588,10 +595,10 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
         if (p.chunk_tiles > 0) chunk = (uint64_t)p.chunk_tiles;  // tuning override
         if (cg == 2)
             e = launch_gemm_round<2>(p.grid, s, tmap_q, tmap_x, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows,
-                                     (uint32_t)total_tiles, (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow);
+                                     (uint32_t)total_tiles, (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow, arrive);
         else
             e = launch_gemm_round<1>(p.grid, s, tmap_q, tmap_x, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows,
-                                     (uint32_t)total_tiles, (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow);
+                                     (uint32_t)total_tiles, (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow, arrive);
         if (e != cudaSuccess) return e;
         if (p.debug_raw_scores) {
             if (p.debug_log_out) *p.debug_log_out = log;
@@ -602,7 +609,7 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
         }
         const bool last = end >= total_tiles;
         select_topk_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, thr, overflow, kSelCap, p.kprime, p.labels,
-                                                      last ? p.final_lists : nullptr, eps_q, p.limit_score);
+                                                      last ? p.final_lists : nullptr, eps_q, p.limit_score, arrive);
         launches += 2;
         begin = end;
         end = end * growth;
