@@ -270,7 +270,9 @@ def test_concurrent_searches_on_one_handle(dawn, oracle):
         idx.add_synthetic(SEED, 0, n)
         stored = oracle.synth_rows_f16(SEED, 0, n)
         far = -oracle.np_synth_rows_f32(77, 0, extra)       # appended rows: irrelevant to the queries below? not guaranteed,
-        shapes = [(1, 10), (2, 20), (40, 10), (130, 100)]   # so appended rows use labels the check filters out
+        shapes = [(1, 10), (2, 20), (300, 10), (520, 100)]  # so appended rows use labels the check filters out
+        # (300 and 520 queries = 2 and 3 query tiles: two tensor-core launches share the SMs here, so the chunk rendezvous of
+        #  gemm_pipe.cuh runs into its timeout instead of its partners -- it must only cost time, never block or change results)
         want = {}
         qsets = {}
         for t, (b, k) in enumerate(shapes):
@@ -309,6 +311,28 @@ def test_concurrent_searches_on_one_handle(dawn, oracle):
         assert not errors, errors[:2]
         assert idx.size() == n + extra
         assert idx.profile()["device_status"] == 0
+
+
+def test_chunk_rendezvous_on_and_off_give_the_same_bits(dawn, oracle):
+    """gemm_unit_sync only changes WHEN the CTA pairs that share a corpus chunk start it (L2 sharing); results are exact either way."""
+    n = 400_000
+    for quant in (dawn.ScalarKind.F16, dawn.ScalarKind.I8):
+        with dawn.new_index(dawn.IndexOptions(capacity=n, quantization=quant)) as idx:
+            idx.add_synthetic(SEED, 0, n)
+            qs = oracle.make_queries(SEED, 77, 700, n)   # 3 query tiles of 256
+            idx.set_option("force_path", 2)
+            idx.set_option("i8_tensor_min_batch", 8)
+            out = []
+            for sync in (1, 0):
+                idx.set_option("gemm_unit_sync", sync)
+                out.append(idx.search_batch(qs, 10))
+            assert (out[0][0] == out[1][0]).all() and (bits(out[0][1]) == bits(out[1][1])).all()
+            if quant == dawn.ScalarKind.F16:
+                stored = oracle.synth_rows_f16(SEED, 0, n)
+                wl, wd, wc, _ = oracle.cpu_scan_f16(stored, None, qs[:64], 10)
+                assert (out[0][0][:64] == wl).all() and (bits(out[0][1][:64]) == bits(wd)).all()
+            p = idx.profile()
+            assert p["gemm_batches"] == 2 and p["uncertified"] == 0
 
 
 def test_device_api_counts_uncertified_results(dawn, oracle):
