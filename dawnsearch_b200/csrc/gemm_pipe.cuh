@@ -257,6 +257,7 @@ __device__ __forceinline__ unsigned long long radix_select_kth(const unsigned lo
             }
             const uint32_t need = *s_need;
             const uint32_t hit = __ballot_sync(0xffffffffu, incl >= need);
+            __syncwarp();  // every lane has read *s_need before the owner of the digit rewrites it (the ballot already orders this; explicit for racecheck)
             if (tid == __ffs(hit) - 1) {
                 uint32_t cum = incl - mine;
                 for (int j = 0; j < 8; j++) {
