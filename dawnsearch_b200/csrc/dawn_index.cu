@@ -1588,11 +1588,21 @@ int dawn_index_load(dawn_index *idx, const char *path) {
         fclose(f);
         return fail(DAWN_ERR_INVALID, "%s holds more than 2^32 rows", path);
     }
-    const size_t rows_alloc = h.size > idx->capacity ? (size_t)h.size : idx->capacity.load();
+    size_t rows_alloc = h.size > idx->capacity ? (size_t)h.size : idx->capacity.load();
     __half *nc = nullptr;
     uint64_t *nl = nullptr;
     float *n32 = nullptr;
-    if (rows_alloc > 0) {
+    // An EMPTY index with room (the start-up case: reserve, then load) is filled in place -- nothing can be lost, and a
+    // second arena next to a pre-reserved 100M-row one would not fit.  Otherwise: fresh arena, swap on success.
+    const bool in_place = idx->size == 0 && idx->phys >= (size_t)h.size && idx->phys > 0;
+    if (in_place) {
+        std::unique_lock<std::shared_mutex> wr(idx->corpus_mu);  // no search may be reading the (empty) arena's pointers
+        wait_device_searches(idx);
+        nc = idx->corpus;
+        nl = idx->labels;
+        n32 = idx->corpus32;
+        rows_alloc = idx->phys;
+    } else if (rows_alloc > 0) {
         rc = alloc_arena(idx, rows_alloc, &nc, &nl, &n32);
         if (rc) {
             fclose(f);
@@ -1634,14 +1644,22 @@ int dawn_index_load(dawn_index *idx, const char *path) {
     idx->stage_busy[0] = idx->stage_busy[1] = false;
     if (ce == cudaSuccess) ce = se;
     if (!ok || ce != cudaSuccess) {
-        cudaFree(nc);
-        cudaFree(nl);
-        cudaFree(n32);
+        if (!in_place) {
+            cudaFree(nc);
+            cudaFree(nl);
+            cudaFree(n32);
+        }
         if (ce != cudaSuccess) {
             cudaGetLastError();
             return fail(DAWN_ERR_IO, "copy to the device failed while loading %s: %s (index unchanged)", path, cudaGetErrorString(ce));
         }
         return fail(DAWN_ERR_IO, "read error on %s (index unchanged)", path);
+    }
+    if (in_place) {
+        idx->size = (size_t)h.size;
+        if (idx->capacity < (size_t)h.size) idx->capacity = (size_t)h.size;
+        reset_norm_stats(idx);
+        return DAWN_OK;
     }
     __half *oc;
     uint64_t *ol;

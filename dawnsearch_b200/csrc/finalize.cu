@@ -243,7 +243,9 @@ finalize_kernel(const __half *__restrict__ corpus, const float *__restrict__ que
     // ---- K6: exact re-score.  The survivors' rows are first staged in shared memory by the whole CTA
     // (coalesced, one round trip to L2/HBM), then one thread per candidate adds the 384 products
     // sequentially in f32 -- the reference's order (vector.rs:128-134).
-    const bool stage_rows = n_lists > 1 && scalar != 2;  // f32 rows (1536 B each) are read in place
+    // f32 rows (1536 B each) are read in place.  A single pre-merged list is read in place too: staging its k' = 128 rows was
+    // measured slower (171 vs 127 us per 1024 queries; 100 KB of shared memory per CTA costs more occupancy than it saves).
+    const bool stage_rows = n_lists > 1 && scalar != 2;
     const int entries = n_lists == 1 ? kp : kFinCapEntries;
     uint8_t *rows_sm = reinterpret_cast<uint8_t *>(sm.s + entries);
     const int stride = scalar ? kRowStrideI8 : kRowStrideF16;

@@ -111,7 +111,10 @@ size_t dawn_index_size(const dawn_index *idx);
 size_t dawn_index_capacity(const dawn_index *idx);
 size_t dawn_index_dimensions(const dawn_index *idx);
 
-/* Persist / restore the stored corpus (fp16 rows + labels) at `path`. */
+/* Persist / restore the stored corpus (rows as stored: f32 / fp16 / int8+scale, and labels) at `path`.
+ * load: an EMPTY index whose reserved capacity covers the file (the start-up sequence reserve -> load) is filled in
+ * place, so a 100M-row shard never needs two arenas; a non-empty index gets a fresh arena that is swapped in only when
+ * the whole file has arrived (a failed load then leaves the index unchanged). */
 int dawn_index_save(dawn_index *idx, const char *path);
 int dawn_index_load(dawn_index *idx, const char *path);
 

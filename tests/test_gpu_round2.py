@@ -254,6 +254,21 @@ def test_failed_load_leaves_the_index_unchanged(dawn, oracle, tmp_path):
             assert (m.labels == wl).all() and (bits(m.distances) == bits(wd)).all()
         idx.load(good)                                       # a good file replaces everything
         assert idx.size() == 10_000 and idx.capacity() >= n
+    # an EMPTY, pre-reserved index (the start-up sequence reserve -> load) is filled in place: no second arena
+    with dawn.new_index(dawn.IndexOptions(capacity=50_000)) as idx:
+        idx.load(good)
+        assert idx.size() == 10_000 and idx.capacity() == 50_000
+        m = idx.search(q, 10)
+        wl, wd = oracle.search_f16(stored[:10_000], labels[:10_000], q, 10)
+        assert (m.labels == wl).all() and (bits(m.distances) == bits(wd)).all()
+        idx.add_batch(labels[10_000:], rows[10_000:])       # and keeps growing from there
+        m = idx.search(q, 10)
+        wl, wd = oracle.search_f16(stored, labels, q, 10)
+        assert (m.labels == wl).all() and (bits(m.distances) == bits(wd)).all()
+    with dawn.new_index(dawn.IndexOptions()) as idx:
+        idx.reserve(n)
+        idx.add_batch(labels[:10_000], rows[:10_000])
+        idx.load(good)
         m = idx.search(q, 10)
         wl, wd = oracle.search_f16(stored[:10_000], labels[:10_000], q, 10)
         assert (m.labels == wl).all() and (bits(m.distances) == bits(wd)).all()
