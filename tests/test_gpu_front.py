@@ -49,6 +49,36 @@ def test_batcher_coalesces_concurrent_callers(dawn, oracle, small):
     b.close()
 
 
+def test_batcher_mixed_k_and_full_batches(dawn, small):
+    """More callers than max_batch, two different k in flight (a batch holds one k; the others wait for the next batch to
+    open), a lone caller afterwards: every answer equals the unbatched dawn_index_search, bit for bit."""
+    idx, rows, stored = small
+    import oracle.oracle as O
+
+    qs = O.make_queries(SEED, 78, 480, len(rows))
+    b = dawn.Batcher(idx, max_batch=16, max_wait_us=500)
+    got = [None] * len(qs)
+
+    def worker(t):
+        for i in range(t, len(qs), 48):
+            got[i] = b.search(qs[i], 20 if (i % 5) else 7)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(48)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for i, m in enumerate(got):
+        want = idx.search(qs[i], 20 if (i % 5) else 7)
+        assert len(m.labels) == len(want.labels)
+        assert (m.labels == want.labels).all() and (bits(m.distances) == bits(want.distances)).all()
+    st = b.stats()
+    assert st["queries"] == len(qs) and st["largest_batch"] <= 16
+    lone = b.search(qs[3], 20)  # one caller: answered without waiting for a window to fill
+    assert (lone.labels == idx.search(qs[3], 20).labels).all()
+    b.close()
+
+
 def test_distance_limit_drops_far_hits(small, oracle):
     idx, rows, stored = small
     q = oracle.make_queries(SEED, 5, 1, len(rows))[0]
