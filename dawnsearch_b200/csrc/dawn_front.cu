@@ -195,7 +195,8 @@ struct dawn_batcher {
         std::string err;
     };
     static constexpr int kRing = 4;
-    dawn_index *idx = nullptr;
+    dawn_index *idx = nullptr;           // exactly one of idx / multi is set
+    dawn_multi *multi = nullptr;
     size_t max_batch = 256;
     uint32_t max_wait_us = 200;
     std::mutex mu;                       // open batch + counters
@@ -265,7 +266,8 @@ struct dawn_batcher {
             b->labels.resize(n * (k ? k : 1));
             b->dist.resize(n * (k ? k : 1));
             b->counts.resize(n);
-            b->rc = dawn_index_search_batch(idx, b->q.data(), n, k, b->labels.data(), b->dist.data(), b->counts.data());
+            b->rc = multi ? dawn_multi_search_batch(multi, b->q.data(), n, k, b->labels.data(), b->dist.data(), b->counts.data())
+                          : dawn_index_search_batch(idx, b->q.data(), n, k, b->labels.data(), b->dist.data(), b->counts.data());
             b->err = b->rc == DAWN_OK ? "" : dawn_last_error();
             gpu.unlock();
             // publish: one wake-up for the whole batch, issued while the other executor's batch is already running
@@ -277,11 +279,12 @@ struct dawn_batcher {
 
 extern "C" {
 
-int dawn_batcher_create(dawn_index *idx, size_t max_batch, uint32_t max_wait_us, dawn_batcher **out) {
-    if (!idx || !out || max_batch == 0) return DAWN_ERR_INVALID;
+static int batcher_create(dawn_index *idx, dawn_multi *multi, size_t max_batch, uint32_t max_wait_us, dawn_batcher **out) {
+    if ((!idx && !multi) || !out || max_batch == 0) return DAWN_ERR_INVALID;
     dawn_batcher *b = new (std::nothrow) dawn_batcher();
     if (!b) return DAWN_ERR_INTERNAL;
     b->idx = idx;
+    b->multi = multi;
     b->max_batch = max_batch;
     b->max_wait_us = max_wait_us;
     for (auto &r : b->ring) {
@@ -291,6 +294,15 @@ int dawn_batcher_create(dawn_index *idx, size_t max_batch, uint32_t max_wait_us,
     for (auto &w : b->workers) w = std::thread([b] { b->run(); });
     *out = b;
     return DAWN_OK;
+}
+
+int dawn_batcher_create(dawn_index *idx, size_t max_batch, uint32_t max_wait_us, dawn_batcher **out) {
+    return batcher_create(idx, nullptr, max_batch, max_wait_us, out);
+}
+
+// The same front over the one-process multi-GPU handle: single-query callers -> batches -> every shard -> merge.
+int dawn_batcher_create_multi(dawn_multi *m, size_t max_batch, uint32_t max_wait_us, dawn_batcher **out) {
+    return batcher_create(nullptr, m, max_batch, max_wait_us, out);
 }
 
 // Blocking and thread-safe: many threads call this with one query each; they are answered in batches.

@@ -192,6 +192,7 @@ def load_library() -> C.CDLL:
     L.dawn_index_get_i24.argtypes = [_vp, C.c_uint64, _vp]
     L.dawn_index_add_page_entries.argtypes = [_vp, _vp, C.c_size_t, C.c_uint64, _vp]
     L.dawn_batcher_create.argtypes = [_vp, C.c_size_t, C.c_uint32, C.POINTER(_vp)]
+    L.dawn_batcher_create_multi.argtypes = [_vp, C.c_size_t, C.c_uint32, C.POINTER(_vp)]
     L.dawn_batcher_search.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp, _vp]
     L.dawn_batcher_stats.argtypes = [_vp, _vp, _vp, _vp]
     L.dawn_batcher_last_error.restype = C.c_char_p
@@ -431,12 +432,16 @@ def decode_i24(data: bytes) -> np.ndarray:  # vector.rs:52-72 (from24); raises i
 
 
 class Batcher:
-    """Micro-batching front: `search` may be called from many threads at once."""
+    """Micro-batching front: `search` may be called from many threads at once.
+    `index` is an Index or a MultiIndex (one process, several GPUs)."""
 
-    def __init__(self, index: "Index", max_batch: int = 256, max_wait_us: int = 200):
+    def __init__(self, index, max_batch: int = 256, max_wait_us: int = 200):
         self._L = load_library()
         h = _vp()
-        _check(self._L.dawn_batcher_create(index._h, max_batch, max_wait_us, C.byref(h)))
+        if isinstance(index, MultiIndex):
+            _check(self._L.dawn_batcher_create_multi(index._h, max_batch, max_wait_us, C.byref(h)))
+        else:
+            _check(self._L.dawn_batcher_create(index._h, max_batch, max_wait_us, C.byref(h)))
         self._h = h
         self._index = index  # keep the index alive
 

@@ -189,10 +189,15 @@ int dawn_index_add_page_entries(dawn_index *idx, const void *entries, size_t n, 
 
 /* Micro-batching front.  The reference answers one query at a time from one thread
  * (src/search/search_service.rs:55-104); a batcher lets any number of threads call
- * dawn_batcher_search concurrently and answers them in batches of up to max_batch queries,
- * waiting at most max_wait_us for a batch to fill.  Results equal dawn_index_search's. */
+ * dawn_batcher_search concurrently and answers them in batches of up to max_batch queries (one k
+ * per batch).  A batch is what arrived while the previous one was on the GPU, plus the callers of
+ * that previous batch if they come back within max_wait_us; a lone caller never waits.  Results
+ * equal dawn_index_search's, bit for bit. */
 typedef struct dawn_batcher dawn_batcher;
 int dawn_batcher_create(dawn_index *idx, size_t max_batch, uint32_t max_wait_us, dawn_batcher **out);
+/* The same front over a dawn_multi handle (below): single-query callers -> batches -> every shard -> merge. */
+struct dawn_multi;
+int dawn_batcher_create_multi(struct dawn_multi *m, size_t max_batch, uint32_t max_wait_us, dawn_batcher **out);
 int dawn_batcher_search(dawn_batcher *b, const float *query384, size_t k, uint64_t *labels_out,
                         float *distances_out, size_t *count_out);
 int dawn_batcher_stats(dawn_batcher *b, uint64_t *batches, uint64_t *queries, uint64_t *largest_batch);

@@ -31,6 +31,7 @@ extern "C" {
     fn dawn_index_search_limit(idx: *mut c_void, q: *const f32, k: usize, distance_limit: f32, labels: *mut u64, dist: *mut f32, count: *mut usize) -> c_int;
     fn dawn_index_search_i24(idx: *mut c_void, q1152: *const u8, k: usize, has_limit: c_int, distance_limit: f32, labels: *mut u64, dist: *mut f32, count: *mut usize) -> c_int;
     fn dawn_batcher_create(idx: *mut c_void, max_batch: usize, max_wait_us: u32, out: *mut *mut c_void) -> c_int;
+    fn dawn_batcher_create_multi(m: *mut c_void, max_batch: usize, max_wait_us: u32, out: *mut *mut c_void) -> c_int;
     fn dawn_batcher_search(b: *mut c_void, q: *const f32, k: usize, labels: *mut u64, dist: *mut f32, count: *mut usize) -> c_int;
     fn dawn_batcher_free(b: *mut c_void);
     fn dawn_index_verify(idx: *mut c_void, bad_rows: *mut usize, min_norm: *mut f32, max_norm: *mut f32) -> c_int;
@@ -203,8 +204,9 @@ impl MultiIndex {
 impl Drop for MultiIndex { fn drop(&mut self) { unsafe { dawn_multi_free(self.m) } } }
 
 /// Micro-batching front for `SearchService` (src/search/search_service.rs:55-104): any number of threads call
-/// `search` with one query each; a worker thread inside the library answers them in batches, which is what feeds the
-/// tensor-core path.  The batcher borrows the index: drop it before the index.
+/// `search` with one query each; the library answers them in batches (what arrived while the previous batch was on the
+/// GPU; a lone caller never waits), which is what feeds the tensor-core path.  The batcher borrows the index: drop it
+/// before the index.
 pub struct Batcher { b: *mut c_void }
 unsafe impl Send for Batcher {}
 unsafe impl Sync for Batcher {}
@@ -212,6 +214,12 @@ impl Batcher {
     pub fn new(index: &Index, max_batch: usize, max_wait_us: u32) -> anyhow::Result<Batcher> {
         let mut b = std::ptr::null_mut();
         ck(unsafe { dawn_batcher_create(index.h, max_batch, max_wait_us, &mut b) })?;
+        Ok(Batcher { b })
+    }
+    /// The same front over the one-process multi-GPU handle.
+    pub fn new_multi(index: &MultiIndex, max_batch: usize, max_wait_us: u32) -> anyhow::Result<Batcher> {
+        let mut b = std::ptr::null_mut();
+        ck(unsafe { dawn_batcher_create_multi(index.m, max_batch, max_wait_us, &mut b) })?;
         Ok(Batcher { b })
     }
     pub fn search(&self, query: &[f32], count: usize) -> anyhow::Result<Matches> {

@@ -79,6 +79,32 @@ def test_batcher_mixed_k_and_full_batches(dawn, small):
     b.close()
 
 
+def test_batcher_over_the_multi_handle(dawn, oracle, small):
+    """dawn_batcher_create_multi: single-query callers -> batches -> two shards (on one GPU here) -> device merge."""
+    idx, rows, stored = small
+    qs = oracle.make_queries(SEED, 79, 96, len(rows))
+    with dawn.MultiIndex([0, 0]) as m:
+        m.reserve(len(rows))
+        m.add_batch(np.arange(1, len(rows) + 1, dtype=np.uint64), rows)
+        b = dawn.Batcher(m, max_batch=32, max_wait_us=500)
+        got = [None] * len(qs)
+
+        def worker(t):
+            for i in range(t, len(qs), 24):
+                got[i] = b.search(qs[i], 10)
+
+        threads = [threading.Thread(target=worker, args=(t,)) for t in range(24)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for i, g in enumerate(got):
+            wl, wd = oracle.search_f16(stored, None, qs[i], 10)
+            assert (g.labels == wl).all() and (bits(g.distances) == bits(wd)).all()
+        assert b.stats()["queries"] == len(qs)
+        b.close()
+
+
 def test_distance_limit_drops_far_hits(small, oracle):
     idx, rows, stored = small
     q = oracle.make_queries(SEED, 5, 1, len(rows))[0]

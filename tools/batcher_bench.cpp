@@ -7,7 +7,8 @@
 //
 // build: g++ -O2 -std=c++17 -I include tools/batcher_bench.cpp -o tools/bin/batcher_bench -L dawnsearch_b200/lib -ldawn_b200
 //        -Wl,-rpath,$PWD/dawnsearch_b200/lib -lpthread
-// usage: batcher_bench <rows> <k> <seconds per point> <max_batch> <max_wait_us> <T,T,...>
+// usage: batcher_bench <rows> <k> <seconds per point> <max_batch> <max_wait_us> <T,T,...> [gpus]
+//        gpus > 1: the corpus is sharded over devices 0..gpus-1 behind one dawn_multi handle (NCCL inside the library)
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -58,21 +59,36 @@ int main(int argc, char **argv) {
             p++;
         }
     }
-    dawn_options o;
-    memset(&o, 0, sizeof o);
-    o.dimensions = 384;
-    o.metric = DAWN_METRIC_IP;
-    o.scalar = DAWN_SCALAR_F16;
-    o.capacity = rows;
+    const int gpus = argc > 7 ? atoi(argv[7]) : 1;
     dawn_index *idx = nullptr;
-    if (dawn_index_create(&o, &idx) != DAWN_OK) {
-        fprintf(stderr, "create: %s\n", dawn_last_error());
-        return 1;
+    dawn_multi *multi = nullptr;
+    if (gpus > 1) {
+        std::vector<int> devs(gpus);
+        for (int g = 0; g < gpus; g++) devs[g] = g;
+        if (dawn_multi_create(devs.data(), devs.size(), DAWN_SCALAR_F16, &multi) != DAWN_OK ||
+            dawn_multi_reserve(multi, rows) != DAWN_OK || dawn_multi_add_synthetic(multi, 0xDA5EA2C4ull, 0, rows) != DAWN_OK) {
+            fprintf(stderr, "multi: %s\n", dawn_multi_last_error());
+            return 1;
+        }
+    } else {
+        dawn_options o;
+        memset(&o, 0, sizeof o);
+        o.dimensions = 384;
+        o.metric = DAWN_METRIC_IP;
+        o.scalar = DAWN_SCALAR_F16;
+        o.capacity = rows;
+        if (dawn_index_create(&o, &idx) != DAWN_OK) {
+            fprintf(stderr, "create: %s\n", dawn_last_error());
+            return 1;
+        }
+        if (dawn_index_add_synthetic(idx, 0xDA5EA2C4ull, 0, rows) != DAWN_OK) {
+            fprintf(stderr, "add_synthetic: %s\n", dawn_last_error());
+            return 1;
+        }
     }
-    if (dawn_index_add_synthetic(idx, 0xDA5EA2C4ull, 0, rows) != DAWN_OK) {
-        fprintf(stderr, "add_synthetic: %s\n", dawn_last_error());
-        return 1;
-    }
+    auto direct = [&](const float *q, uint64_t *l, float *d, size_t *c) {
+        return multi ? dawn_multi_search(multi, q, k, l, d, c) : dawn_index_search(idx, q, k, l, d, c);
+    };
     // --- the reference's pattern: one caller, one query at a time, straight through the index ---
     {
         std::mt19937_64 rng(7);
@@ -83,24 +99,24 @@ int main(int argc, char **argv) {
         std::vector<double> lat;
         for (int i = 0; i < 20; i++) {
             make_query(rng, q.data());
-            dawn_index_search(idx, q.data(), k, l.data(), d.data(), &c);
+            direct(q.data(), l.data(), d.data(), &c);
         }
         const auto t0 = Clock::now();
         while (std::chrono::duration<double>(Clock::now() - t0).count() < secs) {
             make_query(rng, q.data());
             const auto a = Clock::now();
-            if (dawn_index_search(idx, q.data(), k, l.data(), d.data(), &c) != DAWN_OK) return 2;
+            if (direct(q.data(), l.data(), d.data(), &c) != DAWN_OK) return 2;
             lat.push_back(std::chrono::duration<double, std::milli>(Clock::now() - a).count());
         }
         const double el = std::chrono::duration<double>(Clock::now() - t0).count();
-        printf("{\"front\": \"dawn_index_search, one caller\", \"rows\": %zu, \"k\": %zu, \"callers\": 1, \"qps\": %.1f, "
+        printf("{\"front\": \"%s, one caller\", \"gpus\": %d, \"rows\": %zu, \"k\": %zu, \"callers\": 1, \"qps\": %.1f, "
                "\"latency_ms_p50\": %.3f, \"latency_ms_p99\": %.3f}\n",
-               rows, k, lat.size() / el, pct(lat, 0.5), pct(lat, 0.99));
+               multi ? "dawn_multi_search" : "dawn_index_search", gpus, rows, k, lat.size() / el, pct(lat, 0.5), pct(lat, 0.99));
         fflush(stdout);
     }
     for (int T : threads) {
         dawn_batcher *b = nullptr;
-        if (dawn_batcher_create(idx, max_batch, max_wait_us, &b) != DAWN_OK) return 3;
+        if ((multi ? dawn_batcher_create_multi(multi, max_batch, max_wait_us, &b) : dawn_batcher_create(idx, max_batch, max_wait_us, &b)) != DAWN_OK) return 3;
         std::atomic<bool> go{false}, stop{false};
         std::atomic<uint64_t> mismatches{0}, errors{0}, checks{0};
         std::vector<std::vector<double>> lats(T);
@@ -127,7 +143,7 @@ int main(int argc, char **argv) {
                 for (int rep = 0; rep < 2 && t < 64; rep++) {  // parity with the unbatched call, bit for bit
                     make_query(rng, q.data());
                     if (dawn_batcher_search(b, q.data(), k, l.data(), d.data(), &c) != DAWN_OK) errors++;
-                    dawn_index_search(idx, q.data(), k, l2.data(), d2.data(), &c2);
+                    direct(q.data(), l2.data(), d2.data(), &c2);
                     if (c != c2 || memcmp(l.data(), l2.data(), c * 8) || memcmp(d.data(), d2.data(), c * 4)) mismatches++;
                     checks++;
                 }
@@ -146,15 +162,16 @@ int main(int argc, char **argv) {
         for (auto &x : th) x.join();
         std::vector<double> all;
         for (auto &v : lats) all.insert(all.end(), v.begin(), v.end());
-        printf("{\"front\": \"dawn_batcher_search\", \"rows\": %zu, \"k\": %zu, \"callers\": %d, \"max_batch\": %zu, "
+        printf("{\"front\": \"dawn_batcher_search\", \"gpus\": %d, \"rows\": %zu, \"k\": %zu, \"callers\": %d, \"max_batch\": %zu, "
                "\"max_wait_us\": %u, \"qps\": %.1f, \"latency_ms_p50\": %.3f, \"latency_ms_p99\": %.3f, \"mean_batch\": %.1f, "
                "\"largest_batch\": %llu, \"parity_checks\": %llu, \"parity_mismatches\": %llu, \"errors\": %llu}\n",
-               rows, k, T, max_batch, max_wait_us, (q1 - q0) / el, pct(all, 0.5), pct(all, 0.99),
+               gpus, rows, k, T, max_batch, max_wait_us, (q1 - q0) / el, pct(all, 0.5), pct(all, 0.99),
                (double)(q1 - q0) / std::max<uint64_t>(1, b1 - b0), (unsigned long long)m1,
                (unsigned long long)checks.load(), (unsigned long long)mismatches.load(), (unsigned long long)errors.load());
         fflush(stdout);
         dawn_batcher_free(b);
     }
-    dawn_index_free(idx);
+    if (idx) dawn_index_free(idx);
+    if (multi) dawn_multi_free(multi);
     return 0;
 }
