@@ -560,9 +560,11 @@ cudaError_t launch_gemm_search(const GemmSearch &p, cudaStream_t s) {
     // (one query tile: the epilogue has slack) use up to x32 to save rounds.
     // With k' = 128 a x8 round leaves ~900 survivors per query and the epilogue's slow path becomes the
     // bottleneck of the early rounds; x4 measured ~5 % faster at batch 1024, k = 100 (tools/ab_gemm.py).
-    // k' <= 32: x16 (15 k' survivors per query per round fit the log many times over, and every round that is not
-    // launched saves its fixed ~30-40 us: launch, prologue, pipeline fill, select -- profiles/r02_launches_12m5_*.csv).
-    uint64_t growth = p.kprime > 64 ? 4 : (p.kprime > 32 ? 8 : 16);
+    // k' = 16: x16 (every round that is not launched saves its fixed ~30-40 us: launch, prologue, pipeline fill, select --
+    // profiles/r02_launches_12m5_*.csv).  The pattern: a round should leave no more than ~250-400 survivors per query
+    // ((growth - 1) * k'); k' = 32 (the reference's k = 20) at x16 leaves 480 and measured 1-6 % slower than x8 in three
+    // same-box A/Bs on a 12.5M-row shard, no difference at 100M rows (profiles/r02_ab_growth.txt).
+    uint64_t growth = p.kprime > 64 ? 4 : (p.kprime > 16 ? 8 : 16);
     if (n_qtiles == 1 && cg == 1) {
         growth = 32;
         while (growth > 8 && (growth - 1) * (uint64_t)p.kprime * 5 / 4 + (uint64_t)p.kprime > (uint64_t)kSelCap) growth /= 2;
