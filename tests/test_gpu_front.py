@@ -76,6 +76,11 @@ def test_batcher_mixed_k_and_full_batches(dawn, small):
     assert st["queries"] == len(qs) and st["largest_batch"] <= 16
     lone = b.search(qs[3], 20)  # one caller: answered without waiting for a window to fill
     assert (lone.labels == idx.search(qs[3], 20).labels).all()
+    with pytest.raises(dawn.DawnError) as e:  # the index's error reaches the caller of the batch that failed ...
+        b.search(qs[3], 100_000)
+    assert "DAWN_MAX_K" in str(e.value)
+    again = b.search(qs[4], 20)  # ... and the front keeps working
+    assert (again.labels == idx.search(qs[4], 20).labels).all()
     b.close()
 
 
