@@ -1389,9 +1389,11 @@ int dawn_index_search(dawn_index *idx, const float *query384, size_t k, uint64_t
     return dawn_index_search_batch(idx, query384, 1, k, labels_out, distances_out, count_out);
 }
 
-int dawn_index_search_device(dawn_index *idx, const float *d_queries, size_t batch, size_t k,
-                             uint64_t *d_labels_out, float *d_distances_out, uint32_t *d_counts_out,
-                             uint32_t *d_flags_out, void *stream) {
+// (f3) on the device API: the limit is pushed down like in dawn_index_search_batch_limit, and the counts are cut on the
+// device (results ascend, so the filter of udp_service.rs:196-199 truncates) -- what a sharded search needs before its merge.
+int dawn_index_search_device_limit(dawn_index *idx, const float *d_queries, size_t batch, size_t k, float distance_limit,
+                                   uint64_t *d_labels_out, float *d_distances_out, uint32_t *d_counts_out,
+                                   uint32_t *d_flags_out, void *stream) {
     int rc = check_alive(idx);
     if (rc) return rc;
     if (batch == 0) return DAWN_OK;
@@ -1411,14 +1413,17 @@ int dawn_index_search_device(dawn_index *idx, const float *d_queries, size_t bat
         CK(idx, cudaMemsetAsync(d_flags_out, 0x01, batch * sizeof(uint32_t), s));  // bit0: an empty shard's (empty) answer is exact
         return DAWN_OK;
     }
+    const bool limited = distance_limit == distance_limit && distance_limit < INFINITY;
     ws->n_rows = n;
     ws->eps_scale = eps_scale;
-    ws->limit_score = -INFINITY;
+    ws->limit_score = limited ? (float)(1.0 - (double)distance_limit) : -INFINITY;
     // the workspace is shared by all device-API searches on this handle: a search enqueued on another
     // stream than the previous one first waits for it
     if (ws->ws_used && ws->ws_stream != s) CK(idx, cudaStreamWaitEvent(s, ws->ws_done, 0));
     rc = search_enqueue(idx, ws, d_queries, batch, k, choose_kprime(k), d_labels_out, d_distances_out, d_counts_out,
                         d_flags_out, s);
+    if (rc == DAWN_OK && distance_limit == distance_limit)
+        CK(idx, launch_truncate_by_limit(d_distances_out, d_counts_out, batch, k, distance_limit, s));
     if (rc == DAWN_OK) {
         CK(idx, cudaEventRecord(ws->ws_done, s));
         ws->ws_stream = s;
@@ -1426,6 +1431,13 @@ int dawn_index_search_device(dawn_index *idx, const float *d_queries, size_t bat
         ws->counters_clean = true;
     }
     return rc;
+}
+
+int dawn_index_search_device(dawn_index *idx, const float *d_queries, size_t batch, size_t k,
+                             uint64_t *d_labels_out, float *d_distances_out, uint32_t *d_counts_out,
+                             uint32_t *d_flags_out, void *stream) {
+    return dawn_index_search_device_limit(idx, d_queries, batch, k, NAN, d_labels_out, d_distances_out, d_counts_out,
+                                          d_flags_out, stream);
 }
 
 size_t dawn_index_size(const dawn_index *idx) { return idx ? idx->size + idx->staged : 0; }
@@ -2049,6 +2061,22 @@ cudaError_t launch_verify_rows(const void *arena, int scalar, size_t first, size
 }  // namespace
 
 namespace dawn {
+// distance_limit on the device API: results ascend, so "drop distance >= limit" is a cut of the count
+__global__ void truncate_by_limit_kernel(const float *__restrict__ dist, uint32_t *__restrict__ counts, int batch, int k,
+                                         float limit) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const uint32_t c = counts[b];
+    uint32_t keep = 0;
+    while (keep < c && dist[(size_t)b * k + keep] < limit) keep++;
+    counts[b] = keep;
+}
+
+cudaError_t launch_truncate_by_limit(const float *dist, uint32_t *counts, size_t batch, size_t k, float limit, cudaStream_t s) {
+    truncate_by_limit_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, s>>>(dist, counts, (int)batch, (int)k, limit);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_iota_labels(uint64_t *dst, uint64_t first, size_t n, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     size_t blocks = (n + 255) / 256;

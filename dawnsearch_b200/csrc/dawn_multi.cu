@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <cmath>
 #include <mutex>
 #include <new>
 #include <string>
@@ -379,8 +380,11 @@ int dawn_multi_add_synthetic(dawn_multi *m, uint64_t seed, uint64_t first_row, s
     });
 }
 
-int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, size_t k, uint64_t *labels_out,
-                            float *distances_out, size_t *counts_out) {
+// distance_limit (NaN = none): every shard pushes the limit down into its kernels and cuts its counts on the device, so
+// only hits with distance < limit are exchanged and merged (UdpPacket::Search.distance_limit, src/net/udp_packets.rs:29-39;
+// filter src/net/udp_service.rs:196-199).
+int dawn_multi_search_batch_limit(dawn_multi *m, const float *queries, size_t batch, size_t k, float distance_limit,
+                                  uint64_t *labels_out, float *distances_out, size_t *counts_out) {
     if (!m || !queries || !counts_out || (k && (!labels_out || !distances_out))) return DAWN_ERR_INVALID;
     if (batch == 0) return DAWN_OK;
     if (k == 0) {
@@ -458,7 +462,7 @@ int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, s
             return cuda_fail(ce, "H2D queries");
         if ((ce = cudaMemsetAsync(s->d_block, 0, bb, s->stream)) != cudaSuccess) return cuda_fail(ce, "memset block");
         cudaEventRecord(s->ev_a, s->stream);
-        int r = dawn_index_search_device(s->idx, s->d_q, batch, k, reinterpret_cast<uint64_t *>(s->d_block),
+        int r = dawn_index_search_device_limit(s->idx, s->d_q, batch, k, distance_limit, reinterpret_cast<uint64_t *>(s->d_block),
                                          reinterpret_cast<float *>(s->d_block + off_d),
                                          reinterpret_cast<uint32_t *>(s->d_block + off_c), s->d_flags, s->stream);
         if (r) return r;
@@ -474,7 +478,7 @@ int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, s
             for (size_t b = 0; b < batch; b++) {
                 if (s->h_flags[b] & 1u) continue;
                 size_t cnt = 0;
-                r = dawn_index_search(s->idx, queries + b * DAWN_DIMENSIONS, k, l.data(), d.data(), &cnt);
+                r = dawn_index_search_limit(s->idx, queries + b * DAWN_DIMENSIONS, k, distance_limit, l.data(), d.data(), &cnt);
                 if (r) return r;
                 reruns++;
                 uint32_t c32 = (uint32_t)cnt;
@@ -589,6 +593,16 @@ int dawn_multi_get_stats(dawn_multi *m, dawn_multi_stats *out) {
     }
     out->kernel_launches += m->searches + m->nccl_exchanges * m->shards.size();  // merge kernel + NCCL's kernels
     return DAWN_OK;
+}
+
+int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, size_t k, uint64_t *labels_out,
+                            float *distances_out, size_t *counts_out) {
+    return dawn_multi_search_batch_limit(m, queries, batch, k, NAN, labels_out, distances_out, counts_out);
+}
+
+int dawn_multi_search_limit(dawn_multi *m, const float *query384, size_t k, float distance_limit, uint64_t *labels_out,
+                            float *distances_out, size_t *count_out) {
+    return dawn_multi_search_batch_limit(m, query384, 1, k, distance_limit, labels_out, distances_out, count_out);
 }
 
 int dawn_multi_search(dawn_multi *m, const float *query384, size_t k, uint64_t *labels_out, float *distances_out,

@@ -164,6 +164,7 @@ def load_library() -> C.CDLL:
     L.dawn_index_search.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp, _vp]
     L.dawn_index_search_batch.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp]
     L.dawn_index_search_device.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _vp]
+    L.dawn_index_search_device_limit.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, C.c_float, _vp, _vp, _vp, _vp, _vp]
     L.dawn_merge_results_device.argtypes = [C.c_int, _vp, _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t,
                                             C.c_size_t, _vp, _vp, _vp, _vp]
     for name in ("dawn_index_size", "dawn_index_capacity", "dawn_index_dimensions"):
@@ -207,6 +208,8 @@ def load_library() -> C.CDLL:
     L.dawn_multi_add_synthetic.argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_size_t]
     L.dawn_multi_search.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp, _vp]
     L.dawn_multi_search_batch.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp]
+    L.dawn_multi_search_batch_limit.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, C.c_float, _vp, _vp, _vp]
+    L.dawn_multi_search_limit.argtypes = [_vp, _vp, C.c_size_t, C.c_float, _vp, _vp, _vp]
     for name in ("dawn_multi_size", "dawn_multi_capacity", "dawn_multi_shards"):
         getattr(L, name).argtypes = [_vp]
         getattr(L, name).restype = C.c_size_t
@@ -377,10 +380,15 @@ class Index:
         _check(self._L.dawn_index_add_synthetic(self._h, seed, first_row, n))
 
     def search_device(self, d_queries: int, batch: int, count: int, d_labels: int, d_dist: int,
-                      d_counts: int, d_flags: int, stream: int = 0) -> None:
-        """Raw device-pointer entry point (ints are CUDA device addresses); only enqueues."""
-        _check(self._L.dawn_index_search_device(self._h, d_queries, batch, count, d_labels, d_dist,
-                                                d_counts, d_flags, stream))
+                      d_counts: int, d_flags: int, stream: int = 0, distance_limit=None) -> None:
+        """Raw device-pointer entry point (ints are CUDA device addresses); only enqueues.
+        distance_limit: hits with distance >= limit are cut from the counts on the device (udp_service.rs:196-199)."""
+        if distance_limit is None:
+            _check(self._L.dawn_index_search_device(self._h, d_queries, batch, count, d_labels, d_dist,
+                                                    d_counts, d_flags, stream))
+        else:
+            _check(self._L.dawn_index_search_device_limit(self._h, d_queries, batch, count, float(distance_limit), d_labels,
+                                                          d_dist, d_counts, d_flags, stream))
 
     def debug_gemm_score_error(self, queries, acc: "ScoreError") -> None:
         """Accumulate tensor-core score errors over every (query,row) pair (index of <= 2048 rows); see dawn_index.h."""
@@ -541,6 +549,17 @@ class MultiIndex:
         dist = np.zeros((b, max(count, 1)), dtype=np.float32)
         counts = np.zeros(b, dtype=np.uint64)
         self._check(self._L.dawn_multi_search_batch(self._h, _ptr(q), b, count, _ptr(labels), _ptr(dist), _ptr(counts)))
+        return labels, dist, counts.astype(np.int64)
+
+    def search_batch_limit(self, queries, count: int, distance_limit: float):
+        """search_batch with UdpPacket::Search's distance_limit applied on every shard before the exchange."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, EM_LEN)
+        b = q.shape[0]
+        labels = np.zeros((b, max(count, 1)), dtype=np.uint64)
+        dist = np.zeros((b, max(count, 1)), dtype=np.float32)
+        counts = np.zeros(b, dtype=np.uint64)
+        self._check(self._L.dawn_multi_search_batch_limit(self._h, _ptr(q), b, count, float(distance_limit), _ptr(labels),
+                                                          _ptr(dist), _ptr(counts)))
         return labels, dist, counts.astype(np.int64)
 
     def size(self) -> int:

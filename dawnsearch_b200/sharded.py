@@ -106,7 +106,7 @@ class ShardedIndex:
             self._ws[key] = ws
         return ws
 
-    def search_device(self, d_queries: torch.Tensor, k: int, pipelined: bool = False):
+    def search_device(self, d_queries: torch.Tensor, k: int, pipelined: bool = False, distance_limit=None):
         """Queries already on this rank's GPU ([B,384] f32).  Enqueues local search, the all-gather
         and the merge; returns the packed result block (uint8, device) that `ResultBlock.views`
         decodes.
@@ -114,7 +114,10 @@ class ShardedIndex:
         pipelined=False: everything is enqueued on the current stream.
         pipelined=True (back-to-back batches): the exchange + merge of batch i run on a side stream
         while the current stream already searches batch i+1, so the NCCL latency and the wait for the
-        slowest shard are hidden behind compute; call `wait_results()` before reading the block."""
+        slowest shard are hidden behind compute; call `wait_results()` before reading the block.
+
+        distance_limit (UdpPacket::Search, udp_packets.rs:29-39): every shard pushes it into its kernels and cuts its
+        counts on the device, so only hits with distance < limit are exchanged and merged."""
         batch = d_queries.shape[0]
         ws = self._workspace(batch, k)
         blk: ResultBlock = ws["blk"]
@@ -125,12 +128,12 @@ class ShardedIndex:
         if self.world == 1:
             base = ws["local"].data_ptr()
             self.index.search_device(d_queries.data_ptr(), batch, k, base, base + blk.off_dist, base + blk.off_counts,
-                                     base + blk.off_flags, stream)
+                                     base + blk.off_flags, stream, distance_limit)
             return ws["local"]
         if not pipelined:
             base = ws["local"].data_ptr()
             self.index.search_device(d_queries.data_ptr(), batch, k, base, base + blk.off_dist, base + blk.off_counts,
-                                     base + blk.off_flags, stream)
+                                     base + blk.off_flags, stream, distance_limit)
             all_gather_blocks(ws["local"], ws["gathered"], self.group)
             g, o = ws["gathered"].data_ptr(), ws["out"].data_ptr()
             merge_results_device(self.device, g, g + blk.off_dist, g + blk.off_counts, self.world, batch, k,
@@ -156,7 +159,7 @@ class ShardedIndex:
             main.wait_event(pp["merged"][p])
         base = pp["local"][p].data_ptr()
         self.index.search_device(d_queries.data_ptr(), batch, k, base, base + blk.off_dist, base + blk.off_counts,
-                                 base + blk.off_flags, stream)
+                                 base + blk.off_flags, stream, distance_limit)
         pp["searched"][p].record(main)
         side = self._side
         side.wait_event(pp["searched"][p])
@@ -186,7 +189,7 @@ class ShardedIndex:
         merge_results_device(self.device, g, g + blk.off_dist, g + blk.off_counts, self.world, blk.batch, k,
                              o, o + blk.off_dist, o + blk.off_counts, stream, list_stride_bytes=blk.nbytes)
 
-    def search(self, queries: np.ndarray, k: int):
+    def search(self, queries: np.ndarray, k: int, distance_limit=None):
         """Host queries in, host results out (every rank gets the full merged answer).
 
         Exactness across shards: a shard whose certificate failed for a query (near-ties deeper than the
@@ -203,7 +206,7 @@ class ShardedIndex:
             main = torch.cuda.current_stream(self.tdev)
             ws["h_q"].copy_(torch.from_numpy(q))
             ws["q"].copy_(ws["h_q"], non_blocking=True)
-            out = self.search_device(ws["q"], k)
+            out = self.search_device(ws["q"], k, distance_limit=distance_limit)
             ws["h_out"].copy_(out, non_blocking=True)
             if self.world > 1:
                 ws["h_flags"].copy_(blk.flags(ws["gathered"]), non_blocking=True)
@@ -214,7 +217,9 @@ class ShardedIndex:
             if (flags & 1).min() == 0:  # same data on every rank -> same decision on every rank
                 mine = np.nonzero((flags[self.rank] & 1) == 0)[0]
                 if len(mine):
-                    rl, rd, rc = self.index.search_batch(q[mine], k)  # exact: escalates to the f32 scan
+                    # exact: escalates to the f32 scan
+                    rl, rd, rc = (self.index.search_batch(q[mine], k) if distance_limit is None
+                                  else self.index.search_batch_limit(q[mine], k, distance_limit))
                     lab, dist_, cnt = blk.views(ws["local"])
                     sel = torch.from_numpy(mine).to(self.tdev)
                     lab[sel] = torch.from_numpy(rl.view(np.int64)).to(self.tdev)

@@ -137,6 +137,11 @@ int dawn_index_verify(dawn_index *idx, size_t *bad_rows_out, float *min_norm_out
 int dawn_index_search_device(dawn_index *idx, const float *d_queries, size_t batch, size_t k,
                              uint64_t *d_labels_out, float *d_distances_out,
                              uint32_t *d_counts_out, uint32_t *d_flags_out, void *stream);
+/* The same with UdpPacket::Search's distance_limit (NaN = none): pushed down into the kernels' thresholds, and
+ * the counts are cut on the device so that only hits with distance < limit remain (results ascend). */
+int dawn_index_search_device_limit(dawn_index *idx, const float *d_queries, size_t batch, size_t k, float distance_limit,
+                                   uint64_t *d_labels_out, float *d_distances_out,
+                                   uint32_t *d_counts_out, uint32_t *d_flags_out, void *stream);
 /* Merge `n_lists` per-shard result lists (each [batch][k] labels + distances, ascending,
  * with [batch] counts) into one [batch][k] list; the device-side step after the all-gather of
  * a sharded search (the role of search_remote's BestResults merge,
@@ -224,6 +229,11 @@ int dawn_multi_search(dawn_multi *m, const float *query384, size_t k, uint64_t *
                       size_t *count_out);
 int dawn_multi_search_batch(dawn_multi *m, const float *queries, size_t batch, size_t k, uint64_t *labels_out,
                             float *distances_out, size_t *counts_out);
+/* distance_limit across the shards: every shard applies it before the exchange (NaN = none). */
+int dawn_multi_search_limit(dawn_multi *m, const float *query384, size_t k, float distance_limit, uint64_t *labels_out,
+                            float *distances_out, size_t *count_out);
+int dawn_multi_search_batch_limit(dawn_multi *m, const float *queries, size_t batch, size_t k, float distance_limit,
+                                  uint64_t *labels_out, float *distances_out, size_t *counts_out);
 size_t dawn_multi_size(const dawn_multi *m);
 size_t dawn_multi_capacity(const dawn_multi *m);
 size_t dawn_multi_shards(const dawn_multi *m);

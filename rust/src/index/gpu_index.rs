@@ -43,6 +43,7 @@ extern "C" {
     fn dawn_multi_add_batch(m: *mut c_void, labels: *const u64, v: *const f32, n: usize) -> c_int;
     fn dawn_multi_search(m: *mut c_void, q: *const f32, k: usize, labels: *mut u64, dist: *mut f32, count: *mut usize) -> c_int;
     fn dawn_multi_search_batch(m: *mut c_void, q: *const f32, batch: usize, k: usize, labels: *mut u64, dist: *mut f32, counts: *mut usize) -> c_int;
+    fn dawn_multi_search_limit(m: *mut c_void, q: *const f32, k: usize, limit: f32, labels: *mut u64, dist: *mut f32, count: *mut usize) -> c_int;
     fn dawn_multi_size(m: *const c_void) -> usize;
     fn dawn_multi_capacity(m: *const c_void) -> usize;
     fn dawn_multi_shards(m: *const c_void) -> usize;
@@ -187,6 +188,14 @@ impl MultiIndex {
         anyhow::ensure!(query.len() == 384, "query must have 384 dimensions");
         let (mut labels, mut distances, mut n) = (vec![0u64; count], vec![0f32; count], 0usize);
         mck(unsafe { dawn_multi_search(self.m, query.as_ptr(), count, labels.as_mut_ptr(), distances.as_mut_ptr(), &mut n) })?;
+        labels.truncate(n); distances.truncate(n);
+        Ok(Matches { labels, distances })
+    }
+    /// `UdpPacket::Search.distance_limit` (src/net/udp_packets.rs:29-39): every shard applies it before the exchange.
+    pub fn search_limit(&self, query: &[f32], count: usize, distance_limit: f32) -> anyhow::Result<Matches> {
+        anyhow::ensure!(query.len() == 384, "query must have 384 dimensions");
+        let (mut labels, mut distances, mut n) = (vec![0u64; count], vec![0f32; count], 0usize);
+        mck(unsafe { dawn_multi_search_limit(self.m, query.as_ptr(), count, distance_limit, labels.as_mut_ptr(), distances.as_mut_ptr(), &mut n) })?;
         labels.truncate(n); distances.truncate(n);
         Ok(Matches { labels, distances })
     }

@@ -110,6 +110,28 @@ def test_batcher_over_the_multi_handle(dawn, oracle, small):
         b.close()
 
 
+def test_distance_limit_across_shards(dawn, oracle, small):
+    """dawn_multi_search_batch_limit / dawn_index_search_device_limit: every shard applies the limit before the exchange;
+    the merged hits are exactly the oracle's hits with distance < limit, on the scan path and on the tensor-core path."""
+    idx, rows, stored = small
+    qs = oracle.make_queries(SEED, 80, 40, len(rows))
+    with dawn.MultiIndex([0, 0]) as m:
+        m.reserve(len(rows))
+        m.add_batch(np.arange(1, len(rows) + 1, dtype=np.uint64), rows)
+        for force in (1, 2):
+            m.set_option("force_path", force)
+            full_l, full_d, _ = m.search_batch(qs, 20)
+            for limit in (float(np.median(full_d[:, 6])), 0.0, 2.5, float("inf")):
+                gl, gd, gc = m.search_batch_limit(qs, 20, limit)
+                for i, q in enumerate(qs):
+                    wl, wd = oracle.search_f16(stored, None, q, 20)
+                    keep = int((wd < limit).sum())
+                    assert gc[i] == keep
+                    assert (gl[i, :keep] == wl[:keep]).all() and (bits(gd[i, :keep]) == bits(wd[:keep])).all()
+        nan_l, nan_d, nan_c = m.search_batch_limit(qs, 20, float("nan"))  # NaN = no limit
+        assert (nan_c == 20).all() and (nan_l == full_l).all()
+
+
 def test_distance_limit_drops_far_hits(small, oracle):
     idx, rows, stored = small
     q = oracle.make_queries(SEED, 5, 1, len(rows))[0]

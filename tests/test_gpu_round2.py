@@ -50,6 +50,17 @@ for batch, k in ((1, 10), (5, 20), (64, 10), (130, 100)):
         same = (cnt == wc).all() and (gl == wl).all() and (gd.view(np.uint32) == wd.view(np.uint32)).all()
         print("synthetic batch", batch, "k", k, "ok" if same else "MISMATCH", flush=True)
         ok &= bool(same)
+    if batch in (5, 64):  # distance_limit across the shards: every shard cuts before the exchange
+        limit = 0.78
+        ll, ld, lc = sh.search(qs, k, distance_limit=limit)
+        if rank == 0:
+            same = True
+            for i in range(batch):
+                keep = int((wd[i, :wc[i]] < limit).sum())
+                same &= lc[i] == keep and (ll[i, :keep] == wl[i, :keep]).all() and \
+                    (ld[i, :keep].view(np.uint32) == wd[i, :keep].view(np.uint32)).all()
+            print("limit batch", batch, "k", k, "ok" if same else "MISMATCH", flush=True)
+            ok &= bool(same)
 sh.close()
 # duplicates: every shard is full of identical pages, so no shard can certify its top-k from the candidate slack
 # alone -> each re-runs the query exactly before the merge (the hole round 1 left open at N > 1)
@@ -76,6 +87,16 @@ for batch, k in ((1, 10), (24, 20), (24, 100)):
         print("duplicates batch", batch, "k", k, "ok" if same else "MISMATCH", flush=True)
         ok &= bool(same)
         ok &= list(gl[0][:10]) == list(range(1, 11))
+    if batch == 24 and k == 20:  # a limit on top of the exact re-runs
+        limit = 0.5
+        ll, ld, lc = sh.search(qs, k, distance_limit=limit)
+        if rank == 0:
+            same = True
+            for i in range(batch):
+                keep = int((wd[i, :wc[i]] < limit).sum())
+                same &= lc[i] == keep and (ll[i, :keep] == wl[i, :keep]).all()
+            print("limit duplicates ok" if same else "limit duplicates MISMATCH", flush=True)
+            ok &= bool(same)
 t = torch.tensor([escalated], dtype=torch.int64)
 if backend == "nccl":
     t = t.cuda()
@@ -101,7 +122,7 @@ def _run_shard_worker(tmp_path, backend, port):
                         "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        env=env, capture_output=True, text=True, timeout=800)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count(" ok") == 7, r.stdout
+    assert r.stdout.count(" ok") == 10, r.stdout
     assert "MISMATCH" not in r.stdout
 
 
