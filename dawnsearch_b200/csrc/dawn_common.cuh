@@ -92,6 +92,7 @@ cudaError_t launch_gather_f32(const __half *corpus, const uint32_t *rows, size_t
                               cudaStream_t s);
 // labels[i] = first + i (synthetic corpora: label = row + 1, like SQLite rowids, search_provider.rs:275)
 cudaError_t launch_iota_labels(uint64_t *dst, uint64_t first, size_t n, cudaStream_t s);
+cudaError_t launch_shadow_quantize(const __half *corpus, uint8_t *arena, size_t first, size_t n, uint32_t *kappa_bits, cudaStream_t s);
 cudaError_t launch_truncate_by_limit(const float *dist, uint32_t *counts, size_t batch, size_t k, float limit, cudaStream_t s);
 
 struct ScanLaunch {
@@ -244,6 +245,10 @@ struct GemmSearchI8 {
     float eps_scale;          // > 1 when stored rows are longer than the reference's norm gate allows
     const uint32_t **overflow_out;  // out: device pointer to per-query overflow flags
     int *launches_out;        // out: kernels launched
+    // Shadow mode: `arena` is an int8 COPY of the fp16 rows at `rescore_f16` ([n_rows][384]), which hold the truth: the
+    // rounds filter on the copy and re-score on the fp16 rows.  shadow_kappa bounds ||x16 - s_row x8|| / s_row over all rows.
+    const __half *rescore_f16;
+    float shadow_kappa;
 };
 cudaError_t launch_gemm_search_i8(const GemmSearchI8 &p, cudaStream_t s);
 size_t gemm_i8_workspace_bytes(int n_queries);

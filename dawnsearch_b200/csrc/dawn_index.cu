@@ -132,6 +132,13 @@ struct dawn_index {
     __half *corpus = nullptr;      // fp16: [phys][384]; int8: the same pointer holds the blocked arena
     float *corpus32 = nullptr;     // DAWN_SCALAR_F32 only: the vectors as given, [phys][384] f32 (what the exact re-score reads)
     uint64_t *labels = nullptr;
+    // int8 shadow of an fp16 corpus (option "shadow_i8"): a quantised COPY in the blocked int8 layout, used only to FILTER on
+    // the int8 tensor cores / at half the HBM bytes; candidates are re-scored on the fp16 rows, so answers do not change.
+    // Built lazily before a search (rows [shadow_rows, size)), dropped whenever the arena is replaced.
+    std::atomic<uint8_t *> shadow{nullptr};
+    std::atomic<size_t> shadow_rows{0};
+    std::atomic<float> shadow_kappa{0.f};  // max over shadow rows of ||x16 - s_row x8|| / s_row, measured by the quantiser
+    uint32_t *d_shadow_kappa = nullptr;    // device scalar (f32 bits, atomicMax)
     std::atomic<size_t> size{0};      // rows committed to the device
     std::atomic<size_t> capacity{0};  // logical capacity promised to the caller
     size_t phys = 0;                  // rows actually allocated
@@ -178,6 +185,7 @@ struct dawn_index {
     // int8 corpora: batches of at least this many queries take the tensor cores.  0 = never.
     std::atomic<int64_t> i8_tensor_min_batch{16};
     std::atomic<int64_t> i8_tensor_chunk_rows{4 << 20};
+    std::atomic<int64_t> shadow_i8{0};  // 1 = keep an int8 shadow of an fp16 corpus (+388 B per row) and filter on it
     std::atomic<int64_t> i8_native{1};  // 1 = tcgen05 kind::i8 straight from the int8 arena, 0 = dequantise to fp16 tiles
 
     // search workspaces
@@ -281,6 +289,7 @@ void merge_profile(dawn_index *idx, SearchWs *ws) {
     d.kernel_launches += s.kernel_launches;
     d.gemm_batches += s.gemm_batches;
     d.gemm_ms += s.gemm_ms;
+    d.shadow_batches += s.shadow_batches;
     s = dawn_profile{};
 }
 
@@ -348,6 +357,8 @@ inline uint8_t *arena_i8(const dawn_index *idx) { return reinterpret_cast<uint8_
 void wait_device_searches(dawn_index *idx) {
     if (idx->dev_ws && idx->dev_ws->ws_used) cudaEventSynchronize(idx->dev_ws->ws_done);
 }
+
+void drop_shadow(dawn_index *idx);
 
 int alloc_arena(dawn_index *idx, size_t rows, __half **corpus_out, uint64_t **labels_out, float **corpus32_out) {
     __half *nc = nullptr;
@@ -422,6 +433,7 @@ int grow_physical(dawn_index *idx, size_t rows) {
         idx->labels = nl;
         idx->corpus32 = n32;
         idx->phys = want;
+        drop_shadow(idx);
     }
     if (oc) cudaFree(oc);
     if (ol) cudaFree(ol);
@@ -502,6 +514,48 @@ void reset_norm_stats(dawn_index *idx) {
     idx->bad_rows = 0;
     idx->norm_max = 0.f;
     idx->norm_min = INFINITY;
+}
+
+// The arena was replaced (exclusive corpus lock held, no search in flight): the shadow goes with it.
+void drop_shadow(dawn_index *idx) {
+    uint8_t *p = idx->shadow.exchange(nullptr);
+    if (p) cudaFree(p);
+    idx->shadow_rows = 0;
+    idx->shadow_kappa = 0.f;
+}
+
+// Bring the int8 shadow up to date with the fp16 corpus before a search (idx->mu held, stream idle).  Rows are only ever
+// appended, so searches in flight -- which read rows below their own snapshot -- are not disturbed.  A failed allocation
+// switches the option off: the fp16 path answers instead.
+int ensure_shadow(dawn_index *idx) {
+    if (!idx->shadow_i8 || idx->scalar != DAWN_SCALAR_F16) return DAWN_OK;
+    const size_t n = idx->size;
+    if (n < 65536 || idx->shadow_rows >= n) return DAWN_OK;
+    if (!idx->shadow) {
+        const size_t bytes = (idx->phys + kI8BlockRows - 1) / kI8BlockRows * (size_t)kI8BlockBytes;
+        uint8_t *p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess || (!idx->d_shadow_kappa && cudaMalloc(&idx->d_shadow_kappa, 4) != cudaSuccess)) {
+            cudaGetLastError();
+            if (p) cudaFree(p);
+            idx->shadow_i8 = 0;
+            return DAWN_OK;
+        }
+        CK(idx, cudaMemsetAsync(p, 0, bytes, idx->stream));
+        CK(idx, cudaMemsetAsync(idx->d_shadow_kappa, 0, 4, idx->stream));
+        idx->shadow = p;
+        idx->shadow_rows = 0;
+        idx->shadow_kappa = 0.f;
+    }
+    const size_t first = idx->shadow_rows;
+    CK(idx, launch_shadow_quantize(idx->corpus, idx->shadow, first, n - first, idx->d_shadow_kappa, idx->stream));
+    uint32_t bits = 0;
+    CK(idx, cudaMemcpyAsync(&bits, idx->d_shadow_kappa, 4, cudaMemcpyDeviceToHost, idx->stream));
+    CK(idx, cudaStreamSynchronize(idx->stream));
+    float kappa;
+    memcpy(&kappa, &bits, 4);
+    idx->shadow_kappa = kappa * 1.0001f + 1e-4f;
+    idx->shadow_rows = n;
+    return DAWN_OK;
 }
 
 // DAWN_DEBUG_STAGES=1: wait for each kernel of a search separately (polling, 5 s) and say on stderr which one
@@ -798,6 +852,74 @@ int search_i8_native(dawn_index *idx, SearchWs *ws, const float *d_queries, size
     return run_finalize(idx, ws, fl, s, batch);
 }
 
+// fp16 corpus with an int8 shadow (option "shadow_i8"): the rounds FILTER on the shadow with the int8 tensor cores (half the
+// bytes and twice the MMA rate of the fp16 tiles) and rank the survivors by their exact score over the fp16 rows, so the
+// rounds leave the k' best rows by EXACT score and finalize -- the same fp16 re-score as every other path -- orders them.
+int search_f16_shadow(dawn_index *idx, SearchWs *ws, const uint8_t *shadow, float kappa, const float *d_queries, size_t batch,
+                      size_t k, int kprime, uint64_t *d_labels_out, float *d_dist_out, uint32_t *d_counts, uint32_t *d_flags,
+                      cudaStream_t s, uint32_t *d_status_out) {
+    const size_t qp = (batch + 255) / 256 * 256;
+    int rc;
+    {
+        int kp = ((int)k + 4 + 3) / 4 * 4;  // exact scores are ranked: k' = k + 4 is all the certificate needs (see search_i8_native)
+        if (kp < 16) kp = 16;
+        if (kp < kprime) kprime = kp;
+    }
+    if ((rc = ensure_gemm_ws(idx, ws, gemm_i8_workspace_bytes((int)batch)))) return rc;
+    if ((rc = ensure_dev(idx, &ws->d_partials, &ws->partials_cap, qp * kprime))) return rc;
+    if ((rc = prepare_counters(idx, ws, 1, s))) return rc;
+    GemmSearchI8 gs{};
+    gs.arena = shadow;
+    gs.labels = idx->labels;
+    gs.n_rows = ws->n_rows;
+    gs.queries = d_queries;
+    gs.n_queries = (int)batch;
+    gs.kprime = kprime;
+    gs.grid = idx->sm_count;
+    gs.cta_group = (int)idx->gemm_cta_group;
+    gs.chunk_tiles = (int)idx->gemm_chunk_tiles;
+    gs.sequential_tiles = (int)idx->gemm_sequential_tiles;
+    gs.growth = (int)idx->gemm_growth;
+    gs.no_unit_sync = idx->gemm_unit_sync ? 0 : 1;
+    gs.workspace = ws->d_gemm_ws;
+    gs.final_lists = ws->d_partials;
+    gs.limit_score = ws->limit_score;
+    gs.eps_scale = 1.0f;
+    gs.rescore_f16 = idx->corpus;
+    gs.shadow_kappa = kappa;
+    const uint32_t *overflow = nullptr;
+    int launches = 0;
+    gs.overflow_out = &overflow;
+    gs.launches_out = &launches;
+    EventPair evg;
+    bool timedg = begin_event(idx, ws, 2, s, &evg);
+    CK(idx, launch_gemm_search_i8(gs, s));
+    if (timedg) end_event(ws, evg, s);
+    ws->prof.gemm_batches++;
+    ws->prof.shadow_batches++;
+    ws->prof.kernel_launches += launches;
+    FinalizeLaunch fl{};
+    fl.corpus = idx->corpus;
+    fl.queries = d_queries;
+    fl.nq = (int)batch;
+    fl.partials = ws->d_partials;
+    fl.n_lists = 1;
+    fl.kprime = kprime;
+    fl.k = (int)k;
+    fl.eps = 0.f;  // the candidates carry exact scores: a row outside the list scores strictly below its weakest member
+    fl.labels_out = d_labels_out;
+    fl.distances_out = d_dist_out;
+    fl.counts_out = d_counts;
+    fl.flags_out = d_flags;
+    fl.scalar = 0;
+    fl.eps_q = nullptr;
+    fl.overflow = overflow;
+    fl.counters = ws->d_counters;
+    fl.n_counters = 1;
+    fl.status_out = d_status_out;
+    return run_finalize(idx, ws, fl, s, batch);
+}
+
 // Enqueue the whole search for `batch` device-resident queries on stream `s`.  The caller holds the shared
 // corpus lock; ws->n_rows / eps_scale / limit_score describe the snapshot being searched.
 int search_enqueue(dawn_index *idx, SearchWs *ws, const float *d_queries, size_t batch, size_t k, int kprime,
@@ -882,6 +1004,14 @@ int search_enqueue(dawn_index *idx, SearchWs *ws, const float *d_queries, size_t
                           (idx->force_path == 2 ||
                            ((int64_t)batch >= idx->gemm_min_batch && (int64_t)n >= idx->gemm_min_rows) ||
                            ((int64_t)batch >= idx->gemm_small_batch && (int64_t)n >= idx->gemm_small_batch_rows));
+    if (use_gemm && idx->scalar == DAWN_SCALAR_F16 && idx->shadow_i8 && ws->eps_scale == 1.0f && n >= 65536) {
+        // the int8 shadow covers this snapshot (it is brought up to date before every search; rows are append-only)
+        const uint8_t *shadow = idx->shadow.load();
+        const float kappa = idx->shadow_kappa.load();
+        if (shadow && idx->shadow_rows.load() >= n && kappa > 0.f)
+            return search_f16_shadow(idx, ws, shadow, kappa, d_queries, batch, k, kprime, d_labels_out, d_dist_out, d_counts,
+                                     d_flags, s, d_status_out);
+    }
     if (use_gemm) {
         const size_t qp = (batch + 255) / 256 * 256;
         if ((rc = ensure_gemm_ws(idx, ws, gemm_workspace_bytes((int)batch)))) return rc;
@@ -999,6 +1129,8 @@ int snapshot_for_search(dawn_index *idx, std::shared_lock<std::shared_mutex> &rd
     int rc = flush_staged(idx);
     if (rc) return rc;
     rc = ensure_norms_checked(idx);
+    if (rc) return rc;
+    rc = ensure_shadow(idx);
     if (rc) return rc;
     *n_rows = idx->size;
     *eps_scale = eps_scale_of(idx);
@@ -1267,6 +1399,8 @@ void dawn_index_free(dawn_index *idx) {
     if (idx->bulk_ready) bulk_teardown(idx);
     cudaFree(idx->corpus);
     cudaFree(idx->corpus32);
+    cudaFree(idx->shadow.load());
+    cudaFree(idx->d_shadow_kappa);
     cudaFree(idx->labels);
     for (int b = 0; b < 2; b++) {
         cudaFree(idx->d_stage_buf[b]);
@@ -1686,6 +1820,7 @@ int dawn_index_load(dawn_index *idx, const char *path) {
         idx->labels = nl;
         idx->corpus32 = n32;
         idx->phys = rows_alloc;
+        drop_shadow(idx);
         idx->size = (size_t)h.size;
         if (idx->capacity < (size_t)h.size) idx->capacity = (size_t)h.size;
     }
@@ -1782,6 +1917,7 @@ int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value) {
     else if (!strcmp(key, "i8_tensor_min_batch")) idx->i8_tensor_min_batch = value;
     else if (!strcmp(key, "i8_tensor_chunk_rows")) idx->i8_tensor_chunk_rows = value < 65536 ? 65536 : value;
     else if (!strcmp(key, "i8_native")) idx->i8_native = value;
+    else if (!strcmp(key, "shadow_i8")) idx->shadow_i8 = value;
     else return fail(DAWN_ERR_INVALID, "unknown option '%s'", key);
     return DAWN_OK;
 }
@@ -2061,6 +2197,68 @@ cudaError_t launch_verify_rows(const void *arena, int scalar, size_t first, size
 }  // namespace
 
 namespace dawn {
+// int8 shadow of fp16 rows: per-row scale = absmax / 127, x8 = rint(x16 / scale), written in the blocked int8 layout the
+// int8 kernels read (8 rows x 384 B + 8 f32 scales per 3104-byte block).  One warp per row.  kappa_bits collects
+// max ||x16 / s - x8|| over the rows (<= sqrt(384) / 2 = 9.8 in theory, ~5.7-6.3 on real rows): the filter's rigorous
+// bound on a row's own quantisation error is ||q|| * kappa * s_row.
+__global__ void __launch_bounds__(256) shadow_quantize_kernel(const __half *__restrict__ corpus, uint8_t *__restrict__ arena,
+                                                              size_t first, size_t n, uint32_t *__restrict__ kappa_bits) {
+    const int lane = threadIdx.x & 31;
+    const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
+    float kmax = 0.f;
+    for (size_t r = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps) {
+        const size_t row = first + r;
+        const uint2 *src = reinterpret_cast<const uint2 *>(corpus + row * kDim) + lane * 3;  // 12 halfs per lane
+        float x[12];
+        float amax = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const uint2 u = __ldg(src + j);
+            const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+            const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+            x[4 * j] = a.x, x[4 * j + 1] = a.y, x[4 * j + 2] = b.x, x[4 * j + 3] = b.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 12; j++) amax = fmaxf(amax, fabsf(x[j]));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+        if (!(amax < INFINITY)) amax = 0.f;  // a row with inf / NaN cannot be a hit of a normalised query: stored as zeros
+        const float sc = amax > 0.f ? __fdiv_rn(amax, 127.0f) : 1.0f;
+        uint32_t packed[3];
+        float err2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float v = amax > 0.f ? x[4 * j + e] : 0.f;
+                const float t = __fdiv_rn(v, sc);
+                const int qv = max(-127, min(127, (int)rintf(t)));
+                const float d = t - (float)qv;
+                err2 = fmaf(d, d, err2);
+                w |= ((uint32_t)(qv & 0xff)) << (8 * e);
+            }
+            packed[j] = w;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, off);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(arena + i8_row_offset((uint32_t)row)) + lane * 3;
+        dst[0] = packed[0], dst[1] = packed[1], dst[2] = packed[2];
+        if (lane == 0) *reinterpret_cast<float *>(arena + i8_scale_offset((uint32_t)row)) = sc;
+        kmax = fmaxf(kmax, sqrtf(err2) * 1.00001f);
+    }
+    if (lane == 0 && kmax > 0.f) atomicMax(kappa_bits, __float_as_uint(kmax));
+}
+
+cudaError_t launch_shadow_quantize(const __half *corpus, uint8_t *arena, size_t first, size_t n, uint32_t *kappa_bits,
+                                   cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    size_t blocks = (n + 7) / 8;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    shadow_quantize_kernel<<<(unsigned)blocks, 256, 0, s>>>(corpus, arena, first, n, kappa_bits);
+    return cudaGetLastError();
+}
+
 // distance_limit on the device API: results ascend, so "drop distance >= limit" is a cut of the count
 __global__ void truncate_by_limit_kernel(const float *__restrict__ dist, uint32_t *__restrict__ counts, int batch, int k,
                                          float limit) {

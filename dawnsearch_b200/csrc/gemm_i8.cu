@@ -103,7 +103,8 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     const __grid_constant__ CUtensorMap tmap_s, uint32_t tile_begin, uint32_t tile_end, uint32_t n_rows,
                     uint32_t n_tiles_total, uint32_t perm_mult, int n_qtiles, int n_queries, int chunk_tiles,
                     const float *__restrict__ thr_g, uint32_t *__restrict__ cnt_g, uint2 *__restrict__ log_g,
-                    uint32_t *__restrict__ overflow_g, int log_cap, uint32_t *__restrict__ chunk_arrive) {
+                    uint32_t *__restrict__ overflow_g, int log_cap, uint32_t *__restrict__ chunk_arrive,
+                    const float *__restrict__ cq_g) {
     constexpr int kStagesB = kRingTiles32K * CG;
     constexpr int kBRows = BN / CG;                  // corpus rows this CTA streams per tile
     constexpr int kBStageBytes = kBRows * BKB;       // 32 KB or 16 KB
@@ -293,7 +294,10 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const uint32_t chunk = u / (uint32_t)n_qtiles;
             const int q = t * BM * CG + (int)cta_rank * BM + quarter * 32 + lane;
             const bool q_valid = q < n_queries;
-            const float thr = q_valid ? thr_g[q] : __int_as_float(0x7f800000);  // in units of s_row * HI
+            const float thr = q_valid ? thr_g[q] : __int_as_float(0x7f800000);  // in units of s_row * (HI + cq)
+            // shadow mode (the int8 rows are a quantised copy of fp16 rows that hold the truth): the row's own quantisation
+            // error is bounded by ||q|| * kappa * s_row, i.e. by an offset cq = ||q|| * kappa / s1 on HI; 0 for an int8 corpus
+            const float cq = q_valid ? cq_g[q] : 0.0f;
             const bool thr_pos = thr > 0.0f;  // the chunk bound needs a positive threshold (round 0 starts at -inf)
             uint2 *log_q = log_g + (size_t)q * log_cap;
             const uint32_t tile0 = chunk * chunk_tiles;
@@ -335,7 +339,7 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                                  : "r"(gmax_smem + (uint32_t)c * 32u + 16u));
 #pragma unroll
                     for (int g = 0; g < 8; g++) {
-                        if (thr_pos && !(__int2float_rn(m[g]) * gs[g] >= thr)) continue;
+                        if (thr_pos && !((__int2float_rn(m[g]) + cq) * gs[g] >= thr)) continue;
                         float4 s4;
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                      : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w)
@@ -344,7 +348,7 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const int i = 4 * g + j;
-                            const float f = __int2float_rn((int)v[i]) * sc[j];
+                            const float f = (__int2float_rn((int)v[i]) + cq) * sc[j];
                             if (f >= thr && c * 32 + i < lim_tile) {
                                 asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(stage_smem + (n_st * kEpiThreads + col) * 8),
                                              "r"(__float_as_uint(f)), "r"(row0 + half * (BN / 2) + c * 32 + i)
@@ -364,7 +368,7 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         m[g] = max(max((int)v[4 * g], (int)v[4 * g + 1]), max((int)v[4 * g + 2], (int)v[4 * g + 3]));
                     const int mm = max(max(max(m[0], m[1]), max(m[2], m[3])), max(max(m[4], m[5]), max(m[6], m[7])));
                     const float sm_c = __shfl_sync(0xffffffffu, smax, 8 * c);
-                    const bool hit = q_valid && (!thr_pos || __int2float_rn(mm) * sm_c >= thr);
+                    const bool hit = q_valid && (!thr_pos || (__int2float_rn(mm) + cq) * sm_c >= thr);
                     if (hit) examine(v, m, c);
                     __syncwarp();
                 };
@@ -413,11 +417,16 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 }
 
 // ---- query preparation: f32 -> one int8 level hi (padded to whole tiles), s1, and the filter band e1 -----------
+// kappa > 0 = shadow mode: the int8 rows are quantised copies (error norm <= kappa * s_row, measured when they were made) of
+// fp16 rows that hold the truth; cq_g[q] = ||q|| * kappa / s1 is the offset the epilogue adds to HI, and e1 also covers the
+// longer dequantised rows (norm <= 1.0105 + kappa * s_row <= 1.09) and the f32 rounding of the exact sequential sum.
 __global__ void __launch_bounds__(128) prep_queries_i8_gemm_kernel(const float *__restrict__ q32, int n_queries,
                                                                    int8_t *__restrict__ q8, float *__restrict__ s1_g,
-                                                                   float *__restrict__ e1_g) {
+                                                                   float *__restrict__ e1_g, float *__restrict__ cq_g,
+                                                                   float kappa) {
     const int q = blockIdx.x;
     __shared__ float red[4];
+    __shared__ float red2[4];
     float x[3], amax = 0.f;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -430,24 +439,41 @@ __global__ void __launch_bounds__(128) prep_queries_i8_gemm_kernel(const float *
     __syncthreads();
     amax = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
     const float s1 = amax > 0.f ? amax / 127.0f : 1.0f;
-    float err2 = 0.f;
+    float err2 = 0.f, n2 = 0.f;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         const int hi = max(-127, min(127, (int)rintf(x[j] / s1)));
         const float e = fmaf(-s1, (float)hi, x[j]);
         err2 += e * e;
+        n2 = fmaf(x[j], x[j], n2);
         q8[(size_t)q * kDim + threadIdx.x + 128 * j] = (int8_t)hi;
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, off);
+    for (int off = 16; off > 0; off >>= 1) {
+        err2 += __shfl_xor_sync(0xffffffffu, err2, off);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+    }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = err2;
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5] = err2;
+        red2[threadIdx.x >> 5] = n2;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         s1_g[q] = s1;
-        // |sum (q_i - s1 hi_i) x_i| <= ||q - s1 hi|| * ||x||, dequantised rows have norm < 1.02; 1.03 also covers the f32
-        // rounding of this sum of squares; + 3e-6 for the f32 roundings of a = s1 * (s_row * HI) and of thr / s1.
-        e1_g[q] = sqrtf(red[0] + red[1] + red[2] + red[3]) * 1.03f + 3.0e-6f;
+        const float delta = sqrtf(red[0] + red[1] + red[2] + red[3]);
+        if (kappa > 0.0f) {
+            // shadow mode: |q.x16 - s1 s_row HI| <= ||q - s1 hi|| * ||s_row x8|| + ||q|| * ||x16 - s_row x8||; the second term is
+            // row-dependent and lives in cq; 3e-5 = the f32 rounding of the exact sequential sum (<= 384 * 2^-24 * 1.03) plus the
+            // roundings of a and thr / s1
+            e1_g[q] = delta * 1.10f + 3.0e-5f;
+            cq_g[q] = sqrtf(red2[0] + red2[1] + red2[2] + red2[3]) * 1.00001f * kappa / s1;
+        } else {
+            // |sum (q_i - s1 hi_i) x_i| <= ||q - s1 hi|| * ||x||, dequantised rows have norm < 1.02; 1.03 also covers the f32
+            // rounding of this sum of squares; + 3e-6 for the f32 roundings of a = s1 * (s_row * HI) and of thr / s1.
+            e1_g[q] = delta * 1.03f + 3.0e-6f;
+            cq_g[q] = 0.0f;
+        }
     }
 }
 
@@ -464,7 +490,8 @@ __global__ void __launch_bounds__(kSelThreads) select_i8_kernel(uint2 *__restric
                                                                 const float *__restrict__ s1_g, const float *__restrict__ e1_g,
                                                                 float limit_score, float eps_scale,
                                                                 const uint64_t *__restrict__ labels,
-                                                                Cand *__restrict__ final_lists, uint32_t *__restrict__ arrive) {
+                                                                Cand *__restrict__ final_lists, uint32_t *__restrict__ arrive,
+                                                                const __half *__restrict__ corpus16) {
     __shared__ unsigned long long keys[kSelCap];
     clear_arrive_slots(arrive, blockIdx.x, gridDim.x, threadIdx.x, kSelThreads);
     __shared__ unsigned long long s_prefix;
@@ -487,7 +514,22 @@ __global__ void __launch_bounds__(kSelThreads) select_i8_kernel(uint2 *__restric
     for (int i = tid; i < n; i += kSelThreads) {
         const uint2 e = log_q[i];
         float sc = __uint_as_float(e.x);
-        if (i >= kept) {  // exact re-score of a new entry
+        if (i >= kept && corpus16) {  // shadow mode: the truth is the fp16 row -- the oracle's sequential f32 sum over it
+            const uint4 *rp = reinterpret_cast<const uint4 *>(corpus16 + (size_t)e.y * kDim);
+            float acc = 0.0f;
+#pragma unroll 4
+            for (int c = 0; c < kDim / 8; c++) {
+                const uint4 u = __ldg(rp + c);
+                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 x = __half22float2(h[j]);
+                    acc = __fadd_rn(acc, __fmul_rn(sq[c * 8 + 2 * j], x.x));
+                    acc = __fadd_rn(acc, __fmul_rn(sq[c * 8 + 2 * j + 1], x.y));
+                }
+            }
+            sc = acc;
+        } else if (i >= kept) {  // exact re-score of a new entry
             const uint4 *rp = reinterpret_cast<const uint4 *>(arena + i8_row_offset(e.y));
             float acc = 0.0f;
 #pragma unroll 2
@@ -534,7 +576,7 @@ __global__ void __launch_bounds__(kSelThreads) select_i8_kernel(uint2 *__restric
         // filter threshold in the epilogue's units (s_row * HI): a row with a < T - e1 has exact < T
         const float s1 = q < n_queries ? s1_g[q] : 1.0f;
         const float e1 = q < n_queries ? e1_g[q] * eps_scale : 0.f;
-        thr_g[q] = T > __int_as_float(0xff800000) ? (T - e1) / s1 - fabsf((T - e1) / s1) * 2.4e-7f : T;
+        thr_g[q] = T > __int_as_float(0xff800000) ? (T - e1) / s1 - fabsf((T - e1) / s1) * 4.0e-7f : T;
         if (cnt > (uint32_t)log_cap) overflow_g[q] = 1u;
     }
 }
@@ -582,7 +624,7 @@ template <int CG>
 cudaError_t launch_round(int grid, cudaStream_t s, const CUtensorMap &tq, const CUtensorMap &tx, const CUtensorMap &ts,
                          uint32_t tile_begin, uint32_t tile_end, uint32_t n_rows, uint32_t n_tiles_total, uint32_t perm_mult,
                          int n_qtiles, int n_queries, int chunk, const float *thr, uint32_t *cnt, uint2 *log,
-                         uint32_t *overflow, uint32_t *arrive) {
+                         uint32_t *overflow, uint32_t *arrive, const float *cq) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kI8Threads);
@@ -597,14 +639,14 @@ cudaError_t launch_round(int grid, cudaStream_t s, const CUtensorMap &tq, const 
     cfg.numAttrs = 1;
     int log_cap = kSelCap;
     return cudaLaunchKernelEx(&cfg, gemm_i8_topk_kernel<CG>, tq, tx, ts, tile_begin, tile_end, n_rows, n_tiles_total, perm_mult,
-                              n_qtiles, n_queries, chunk, thr, cnt, log, overflow, log_cap, arrive);
+                              n_qtiles, n_queries, chunk, thr, cnt, log, overflow, log_cap, arrive, cq);
 }
 
 }  // namespace
 
 size_t gemm_i8_workspace_bytes(int n_queries) {
     const size_t qp = ((size_t)n_queries + 2 * BM - 1) / (2 * BM) * (2 * BM);
-    return qp * kDim + qp * (6 * sizeof(float)) + qp * (size_t)kSelCap * sizeof(uint2) + 1024 + kArriveSlots * sizeof(uint32_t);
+    return qp * kDim + qp * (7 * sizeof(float)) + qp * (size_t)kSelCap * sizeof(uint2) + 1024 + kArriveSlots * sizeof(uint32_t);
 }
 
 cudaError_t launch_gemm_search_i8(const GemmSearchI8 &p, cudaStream_t s) {
@@ -631,6 +673,8 @@ cudaError_t launch_gemm_search_i8(const GemmSearchI8 &p, cudaStream_t s) {
     w += (size_t)qp * sizeof(uint32_t);
     uint32_t *overflow = reinterpret_cast<uint32_t *>(w);
     w += (size_t)qp * sizeof(uint32_t);
+    float *cq = reinterpret_cast<float *>(w);
+    w += (size_t)qp * sizeof(float);
     w = reinterpret_cast<uint8_t *>(((uintptr_t)w + 255) & ~(uintptr_t)255);
     uint2 *log = reinterpret_cast<uint2 *>(w);
     uint32_t *arrive = (n_qtiles > 1 && !p.no_unit_sync) ? reinterpret_cast<uint32_t *>(w + (size_t)qp * kSelCap * sizeof(uint2)) : nullptr;
@@ -653,16 +697,21 @@ cudaError_t launch_gemm_search_i8(const GemmSearchI8 &p, cudaStream_t s) {
 
     cudaError_t e;
     if ((e = cudaMemsetAsync(cnt, 0, (size_t)qp * 3 * sizeof(uint32_t), s)) != cudaSuccess) return e;  // cnt, kept, overflow
-    prep_queries_i8_gemm_kernel<<<qp, 128, 0, s>>>(p.queries, p.n_queries, q8, s1, e1);
+    const float kappa = p.rescore_f16 ? p.shadow_kappa : 0.0f;
+    if (p.rescore_f16 && !(kappa > 0.0f)) return cudaErrorInvalidValue;
+    prep_queries_i8_gemm_kernel<<<qp, 128, 0, s>>>(p.queries, p.n_queries, q8, s1, e1, cq, kappa);
     // thresholds before the first round: -inf, or the pushed-down limit (a select pass over empty logs)
     select_i8_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, kept, thr, overflow, kSelCap, p.kprime, p.arena, p.queries,
-                                                p.n_queries, s1, e1, p.limit_score, p.eps_scale, p.labels, nullptr, arrive);
+                                                p.n_queries, s1, e1, p.limit_score, p.eps_scale, p.labels, nullptr, arrive,
+                                                p.rescore_f16);
     int launches = 2;
     // Rounds grow x8 (x4 for k' = 128): the filter band e1 lets ~2x more rows through than an exact threshold would,
     // (growth - 1) * k' * 2.2 + k' entries must fit the 2048-entry log with margin.
+    // Shadow mode: the band also holds the rows' own quantisation error (~5x the survivors of an exact threshold).
     uint64_t growth = p.kprime > 64 ? 4 : 8;
     if (p.growth >= 2) growth = (uint64_t)p.growth;
-    while (growth > 2 && (growth - 1) * (uint64_t)p.kprime * 11 / 4 + (uint64_t)p.kprime > (uint64_t)kSelCap) growth /= 2;
+    const uint64_t band_x4 = p.rescore_f16 ? 22 : 11;  // survivors per exact-threshold survivor, in quarters
+    while (growth > 2 && (growth - 1) * (uint64_t)p.kprime * band_x4 / 4 + (uint64_t)p.kprime > (uint64_t)kSelCap) growth /= 2;
     const uint64_t total_tiles = (p.n_rows + BN - 1) / BN;
     uint64_t mult = (uint64_t)((double)total_tiles * 0.6180339887498949) | 1ull;
     auto gcd = [](uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; };
@@ -680,15 +729,15 @@ cudaError_t launch_gemm_search_i8(const GemmSearchI8 &p, cudaStream_t s) {
         if (p.chunk_tiles > 0) chunk = (uint64_t)p.chunk_tiles;
         if (cg == 2)
             e = launch_round<2>(p.grid, s, tq, tx, ts, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows, (uint32_t)total_tiles,
-                                (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow, arrive);
+                                (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow, arrive, cq);
         else
             e = launch_round<1>(p.grid, s, tq, tx, ts, (uint32_t)begin, (uint32_t)end, (uint32_t)p.n_rows, (uint32_t)total_tiles,
-                                (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow, arrive);
+                                (uint32_t)mult, n_qtiles, p.n_queries, (int)chunk, thr, cnt, log, overflow, arrive, cq);
         if (e != cudaSuccess) return e;
         const bool last = end >= total_tiles;
         select_i8_kernel<<<qp, kSelThreads, 0, s>>>(log, cnt, kept, thr, overflow, kSelCap, p.kprime, p.arena, p.queries,
                                                     p.n_queries, s1, e1, p.limit_score, p.eps_scale, p.labels,
-                                                    last ? p.final_lists : nullptr, arrive);
+                                                    last ? p.final_lists : nullptr, arrive, p.rescore_f16);
         launches += 2;
         begin = end;
         end = end * growth;

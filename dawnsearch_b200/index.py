@@ -75,6 +75,7 @@ class Profile(C.Structure):
         ("device_uncertified", C.c_uint64),
         ("device_status", C.c_uint64),
         ("max_selection_error", C.c_double),
+        ("shadow_batches", C.c_uint64),
     ]
 
     def as_dict(self):

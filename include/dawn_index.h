@@ -273,6 +273,7 @@ typedef struct dawn_profile {
     /* Largest |selection score - exact re-score| over every candidate any finalize launch has handled since the last reset
      * (all paths).  The certificate's eps constants must stay above it: tests/test_gpu_slack.py. */
     double max_selection_error;
+    uint64_t shadow_batches; /* of gemm_batches: fp16 corpus answered through its int8 shadow (option "shadow_i8") */
 } dawn_profile;
 /* enable != 0: record CUDA events around every K2 / finalize launch (adds host syncs when
  * read).  Off by default. */
@@ -281,6 +282,9 @@ int dawn_index_set_profiling(dawn_index *idx, int enable);
  * batch takes the tensor-core path instead of repeated streaming scans; "force_path" 0 = auto,
  * 1 = scan only, 2 = tensor-core path whenever the corpus holds >= 1024 vectors.
  * "gemm_small_batch" (2) / "gemm_small_batch_rows" (2M): on big corpora even small batches take the tensor-core path (fp16 and int8).
+ * "shadow_i8" (0): 1 = an fp16 corpus also keeps an int8 copy of itself (+388 B per row, built lazily before a search) and
+ * batches that would take the fp16 tensor-core path are FILTERED on the copy by the int8 tensor cores instead -- half the
+ * HBM bytes, twice the MMA rate -- while every candidate is re-scored on the fp16 rows: results stay bit-identical.
  * int8 corpora: "i8_tensor_min_batch" (16, 0 = never) -- from this batch size on the corpus is dequantised chunk by chunk
  * ("i8_tensor_chunk_rows", 4M) into an fp16 scratch and searched on the tensor cores; results stay bit-identical.
  * "gemm_cta_group", "gemm_chunk_tiles", "gemm_growth", "gemm_sequential_tiles": A/B knobs of the tensor-core path, 0 = automatic;

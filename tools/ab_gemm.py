@@ -14,6 +14,8 @@ settings = [{knob: v} for v in values]
 scalar = os.environ.get("DAWN_AB_SCALAR", "f16")
 idx = D.new_index(D.IndexOptions(capacity=rows, quantization=D.ScalarKind.I8 if scalar == "i8" else D.ScalarKind.F16))
 idx.add_synthetic(0xDA5EA2C4, 0, rows)
+if os.environ.get("DAWN_AB_SHADOW", "0") == "1":
+    idx.set_option("shadow_i8", 1)  # fp16 corpus filtered through its int8 copy
 dev = torch.device("cuda:0")
 q = torch.from_numpy(synth.make_queries(0xDA5EA2C4, 3, batch, rows)).to(dev)
 L = torch.zeros((batch, k), dtype=torch.int64, device=dev); Dd = torch.zeros((batch, k), dtype=torch.float32, device=dev)
