@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=1024, help="queries per step")
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--scalar", default="f16", choices=["f16", "i8"], help="stored precision of the corpus")
+    ap.add_argument("--no-shadow", action="store_true",
+                    help="fp16 corpus: do not keep the int8 shadow copy (option shadow_i8); batches then run on the fp16 tensor-core tiles")
     ap.add_argument("--latency-steps", type=int, default=200, help="batch-1 steps for the latency section (0 = skip)")
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -283,6 +285,12 @@ def run_ours(args):
     first, n_local = shard_range(rank, world, args.rows)
     row_bytes = ROW_BYTES if args.scalar == "f16" else 388  # i8: 384 B + f32 scale
     sh = ShardedIndex(local, max(n_local, 1), quantization=0 if args.scalar == "f16" else 1)
+    # fp16 corpus + int8 shadow (library option "shadow_i8", +388 B per row): batches are FILTERED on the int8 copy by the int8
+    # tensor cores and every candidate is re-scored on the fp16 rows -- the answers are the exact top-k over the fp16 vectors,
+    # bit for bit (the parity check below runs with the same option), at half the corpus bytes and twice the MMA rate.
+    shadow = args.scalar == "f16" and not args.no_shadow
+    if shadow:
+        sh.index.set_option("shadow_i8", 1)
     t0 = time.perf_counter()
     sh.index.add_synthetic(SEED, first, n_local)
     fill_s = time.perf_counter() - t0
@@ -359,21 +367,38 @@ def run_ours(args):
 
     def roofline_of(prof, batch, peaks):
         """Roofline of the dominant kernel of a device-resident run."""
+        if prof["gemm_batches"] and batch < 128:
+            # one query tile: the rounds stream the corpus (its int8 shadow, or the int8 corpus) once per batch -> HBM-bound
+            gms = prof["gemm_ms"] / int(prof["gemm_batches"])
+            rb = 388 if (args.scalar == "i8" or prof.get("shadow_batches")) else row_bytes
+            algo = n_local * rb
+            ach = algo / (gms / 1e3) / 1e9
+            ratio = ncu_traffic_ratio("gemm_i8_topk_kernel<2> final round" if rb == 388 else "gemm_topk_kernel<2> final round")
+            return {"bound": "hbm", "kernel": ("gemm_i8_topk_kernel<1> (one query tile; all rounds of a batch incl. the exact re-score selects)"
+                                               + (" over the int8 shadow of the fp16 corpus" if prof.get("shadow_batches") else ""))
+                                              if rb == 388 else "gemm_topk_kernel<1> (one query tile; all rounds of a batch incl. select)",
+                    "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                    "traffic": ratio * algo if ratio else None,
+                    "traffic_note": "DRAM ratio of the CTA-pair kernel's capture (profiles/ncu_summary.json) x this batch's algorithmic bytes",
+                    "peak_source": peaks["source"] + " hbm_gbs", "frac_of_nominal_8TBs": ach / 8000.0,
+                    "algorithmic_bytes_per_batch": algo, "avg_batch_ms": gms, "avg_launch_ms": gms, "batches_timed": int(prof["gemm_batches"])}
         if prof["gemm_batches"]:
             gms = prof["gemm_ms"] / int(prof["gemm_batches"])
             flops = 2.0 * batch * n_local * DIM
             ach = flops / (gms / 1e3) / 1e12
-            if args.scalar == "i8":
+            if args.scalar == "i8" or prof.get("shadow_batches"):
                 # int8 tensor path (tcgen05 kind::i8): MEASURED_PEAKS.json holds no int8 figure; the int8 pipe is specified at
                 # twice the bf16 rate (4.5 vs 2.25 POP/s dense), so the denominator is 2 x the measured sustained bf16 peak
                 peak = 2.0 * peaks["tf_sustained"]
                 ratio = ncu_traffic_ratio("gemm_i8_topk_kernel<2> final round")
-                return {"bound": "tensor", "kernel": "gemm_i8_topk_kernel (tcgen05 kind::i8; all rounds of a batch incl. the exact re-score selects)",
+                i8_bytes = 388  # what the int8 kernel streams per row (the shadow copy of an fp16 corpus, or the int8 corpus itself)
+                return {"bound": "tensor", "kernel": "gemm_i8_topk_kernel (tcgen05 kind::i8; all rounds of a batch incl. the exact re-score selects)"
+                                                     + (" over the int8 shadow of the fp16 corpus" if args.scalar == "f16" else ""),
                         "achieved": ach, "peak": peak, "unit": "TOP/s (int8)", "frac": ach / peak,
-                        "traffic": ratio * n_local * row_bytes if ratio else None,
+                        "traffic": ratio * n_local * i8_bytes if ratio else None,
                         "peak_source": "2 x " + peaks["source"] + " bf16_tflops_sustained (no measured int8 peak on this pool; the int8 pipe is rated at 2x bf16)",
                         "frac_of_nominal_4500": ach / 4500.0, "algorithmic_ops_per_batch": flops, "avg_batch_ms": gms,
-                        "corpus_stream_gbps": n_local * row_bytes / (gms / 1e3) / 1e9}
+                        "corpus_stream_gbps": n_local * i8_bytes / (gms / 1e3) / 1e9}
             ratio = ncu_traffic_ratio("gemm_topk_kernel<2> final round")
             return {"bound": "tensor", "kernel": "gemm_topk_kernel (tcgen05; all rounds of a batch incl. select)",
                     "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
@@ -417,6 +442,8 @@ def run_ours(args):
         p_rows = min(args.rows, args.parity_rows if args.scalar == "f16" else min(args.parity_rows, 200_000))
         pf, pn = shard_range(rank, world, p_rows)
         shp = ShardedIndex(local, max(pn, 1), quantization=0 if args.scalar == "f16" else 1)
+        if shadow:
+            shp.index.set_option("shadow_i8", 1)
         shp.index.add_synthetic(SEED, pf, pn)
         pq = O.make_queries(SEED, SEED + 99, 64, p_rows, planted_fraction=0.25)
         got = shp.search(pq, k)
@@ -428,7 +455,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         from dawnsearch_b200.sharded import ResultBlock
         dl, dd, dc = ResultBlock(64, k).views(blk_dev.cpu())
-        dev_unc = allsum(shp.index.profile()["device_uncertified"])
+        pprof = shp.index.profile()
+        dev_unc = allsum(pprof["device_uncertified"])
+        shadow_used = allsum(pprof["shadow_batches"])
         if rank == 0:
             if args.scalar == "f16":
                 stored = CK.synth_rows_f16(SEED, 0, p_rows)
@@ -448,6 +477,7 @@ def run_ours(args):
                       "bit_identical": same_host and same_one and same_dev,
                       "host_path_batch64": same_host, "host_path_single_query": same_one, "device_pipelined_path": same_dev,
                       "escalated_to_exact_scan": int(esc), "device_path_uncertified": int(dev_unc),
+                      "batches_through_the_int8_shadow_all_ranks": int(shadow_used),
                       "checker": "oracle/cpu_scan.c dawn_cpu_scan_f16" if args.scalar == "f16" else "oracle/dawn_oracle.c dawn_oracle_search_i8"}
             assert parity["bit_identical"], f"parity check failed: {parity}"
         shp.close()
@@ -476,6 +506,16 @@ def run_ours(args):
     prof_e2e = sh.index.profile(reset=True)
     e2e_escalated = int(allsum(prof_e2e["escalations"] + e2e_esc[0]))
 
+    # ---- the same batches on the fp16 tensor-core tiles (shadow off), a few steps, for the record ----
+    fp16_tiles = None
+    if shadow and prof.get("shadow_batches"):
+        sh.index.set_option("shadow_i8", 0)
+        t_ms, _, pf16, _ = timed_device(pool_dev, k, min(K, 5), 2)
+        sh.index.set_option("shadow_i8", 1)
+        fp16_tiles = {"value": B * min(K, 5) / (t_ms / 1e3), "unit": "queries/s", "ms_per_step": t_ms / min(K, 5), "steps": min(K, 5),
+                      "note": "option shadow_i8 off: gemm_topk_kernel (tcgen05 kind::f16 tiles straight from the fp16 rows)",
+                      "roofline": roofline_of(pf16, B, peaks)}
+
     # sanity: a planted neighbour must come back first (a wrong kernel cannot post a number)
     planted = O.planted_rows(SEED + 1, B, args.rows, 0.25)
     if len(planted):
@@ -494,9 +534,12 @@ def run_ours(args):
             ent = {"batch": sb, "k": sk, "qps": sb / (ms / 1e3), "ms_per_step": ms,
                    "finalize_ms": p["finalize_ms"] / max(int(p["finalize_launches"]), 1)}
             r = roofline_of(p, sb, peaks)
-            if p["gemm_batches"]:
-                ent.update({"path": "tcgen05", "gemm_ms": r["avg_batch_ms"], "tflops": r["achieved"],
-                            "corpus_gbps": r["corpus_stream_gbps"]})
+            if p["gemm_batches"] and r["bound"] == "hbm":
+                ent.update({"path": "tcgen05 (int8 shadow)" if p.get("shadow_batches") else "tcgen05", "gemm_ms": r["avg_batch_ms"],
+                            "corpus_gbps": r["achieved"]})
+            elif p["gemm_batches"]:
+                ent.update({"path": "tcgen05 (int8 shadow)" if p.get("shadow_batches") else "tcgen05", "gemm_ms": r["avg_batch_ms"],
+                            "tflops": r["achieved"], "corpus_gbps": r["corpus_stream_gbps"]})
             else:
                 ent.update({"path": "scan", "scan_passes": int(p["scan_launches"]) // 10,
                             "scan_ms_per_pass": r["avg_launch_ms"], "scan_gbps": r["achieved"]})
@@ -507,13 +550,16 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": ("f16 x f16 -> f32 (tensor cores) / f32 scan, exact f32 re-score" if args.scalar == "f16" else
+            "scaling": "strong", "vs_baseline": None, "dtype": ("s8 x s8 -> s32 filter on an int8 shadow (tensor cores) / f32 scan, exact f32 re-score over the fp16 rows" if shadow else
+                                                          "f16 x f16 -> f32 (tensor cores) / f32 scan, exact f32 re-score" if args.scalar == "f16" else
                                                           "s8 x s8 -> s32 (tensor cores) / dp4a scan, exact f32 re-score"),
             "data": "synthetic",
             "config": {"workload": workload_name(args), "rows": args.rows, "rows_per_gpu": n_local,
                        "batch": B, "k": k, "l2": "inputs larger than L2 (corpus shard >> 126 MB), no flush",
                        "multi_gpu": ("device-resident `value`: the all-gather + merge of batch i run on a side stream "
                                      "while batch i+1 is searched; e2e: synchronous per call") if world > 1 else None,
+                       "int8_shadow": ("on: +388 B per row beside the 768 B fp16 row (library option shadow_i8); filter only, "
+                                       "answers are exact over the fp16 rows") if shadow else None,
                        "corpus_fill_s": round(fill_s, 3)},
             "latency_ms": {"device_step_p50": statistics.median(step_ms), "device_step_max": max(step_ms),
                            "e2e_step_p50": statistics.median(lat),
@@ -532,6 +578,8 @@ def run_ours(args):
                                   "scan before the merge (N = 1: inside dawn_index_search_batch; N > 1: ShardedIndex.search)"},
             "parity_check": parity,
         }
+        if fp16_tiles:
+            line["fp16_tensor_path"] = fp16_tiles
         if batch1:
             line["batch1"] = batch1
         if sweep:
@@ -559,12 +607,15 @@ def run_multi(args):
     G, B, k, K, W = args.gpus, args.batch, args.k, args.steps, args.warmup
     scalar = 0 if args.scalar == "f16" else 1
     row_bytes = ROW_BYTES if args.scalar == "f16" else 388
+    shadow = args.scalar == "f16" and not args.no_shadow  # see run(): int8 shadow of the fp16 corpus, filter only
     parity = None
     if not args.no_parity_check:
         from oracle import oracle as CK  # checker only
 
         p_rows = min(args.rows, args.parity_rows)
         with D.MultiIndex(list(range(G)), quantization=0) as mp:
+            if shadow:
+                mp.set_option("shadow_i8", 1)
             mp.reserve(p_rows)
             mp.add_synthetic(SEED, 0, p_rows)
             pq = O.make_queries(SEED, SEED + 99, 64, p_rows, planted_fraction=0.25)
@@ -581,6 +632,8 @@ def run_multi(args):
                       "exchange_modes": ok, "stats": mp.stats(), "checker": "oracle/cpu_scan.c dawn_cpu_scan_f16"}
             assert parity["bit_identical"], parity
     m = D.MultiIndex(list(range(G)), quantization=scalar)
+    if shadow:
+        m.set_option("shadow_i8", 1)
     m.reserve(args.rows)
     t0 = time.perf_counter()
     m.add_synthetic(SEED, 0, args.rows)
@@ -622,7 +675,8 @@ def run_multi(args):
     line = {
         "metric": METRIC, "value": B * K / (sum(dev_ms) / 1e3), "unit": "queries/s", "n_gpus": G, "steps": K, "warmup": W,
         "ms_per_step": sum(dev_ms) / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f16 x f16 -> f32 (tensor cores) / f32 scan, exact f32 re-score", "data": "synthetic",
+        "dtype": ("s8 x s8 -> s32 filter on an int8 shadow (tensor cores) / f32 scan, exact f32 re-score over the fp16 rows" if shadow
+                  else "f16 x f16 -> f32 (tensor cores) / f32 scan, exact f32 re-score"), "data": "synthetic",
         "config": {"workload": workload_name(args), "front": "multi: one process, dawn_multi_* C ABI, NCCL all-gather inside the library",
                    "rows": args.rows, "rows_per_gpu": (args.rows + G - 1) // G, "batch": B, "k": k,
                    "l2": "inputs larger than L2 (corpus shard >> 126 MB), no flush", "corpus_fill_s": round(fill_s, 3),
@@ -634,8 +688,11 @@ def run_multi(args):
         "exchange_ab": out_modes, "multi_stats": st, "gpu_launches": int(st["kernel_launches"]),
         "roofline": {"bound": "tensor" if B >= 256 else "hbm", "note": "per-kernel rooflines are reported by the default front; "
                      "this front reports the whole call", "achieved": 2.0 * B * args.rows * DIM / (statistics.median(dev_ms) / 1e3) / 1e12 / G,
-                     "unit": "TFLOP/s per GPU (whole call)", "peak": measured_peaks()["tf_sustained"],
-                     "frac": 2.0 * B * args.rows * DIM / (statistics.median(dev_ms) / 1e3) / 1e12 / G / measured_peaks()["tf_sustained"],
+                     "unit": ("TOP/s (int8) per GPU (whole call); peak = 2 x measured sustained bf16" if (shadow or args.scalar == "i8")
+                              else "TFLOP/s per GPU (whole call)"),
+                     "peak": measured_peaks()["tf_sustained"] * (2.0 if (shadow or args.scalar == "i8") else 1.0),
+                     "frac": 2.0 * B * args.rows * DIM / (statistics.median(dev_ms) / 1e3) / 1e12 / G /
+                             (measured_peaks()["tf_sustained"] * (2.0 if (shadow or args.scalar == "i8") else 1.0)),
                      "traffic": None, "corpus_stream_gbps_per_gpu": args.rows / G * row_bytes / (statistics.median(dev_ms) / 1e3) / 1e9},
         "clocks": clocks, "parity_check": parity,
     }

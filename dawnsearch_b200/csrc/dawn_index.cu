@@ -186,6 +186,7 @@ struct dawn_index {
     std::atomic<int64_t> i8_tensor_min_batch{16};
     std::atomic<int64_t> i8_tensor_chunk_rows{4 << 20};
     std::atomic<int64_t> shadow_i8{0};  // 1 = keep an int8 shadow of an fp16 corpus (+388 B per row) and filter on it
+    std::atomic<int64_t> shadow_single_rows{6000000};  // with a shadow: from this many rows on, single queries take it too
     std::atomic<int64_t> i8_native{1};  // 1 = tcgen05 kind::i8 straight from the int8 arena, 0 = dequantise to fp16 tiles
 
     // search workspaces
@@ -1000,18 +1001,25 @@ int search_enqueue(dawn_index *idx, SearchWs *ws, const float *d_queries, size_t
         return run_finalize(idx, ws, fl, s, batch);
     }
     const bool gemm_ok = n >= 1024 && batch >= 1;
+    // the int8 shadow covers this snapshot (it is brought up to date before every search; rows are append-only)
+    const uint8_t *shadow = nullptr;
+    float kappa = 0.f;
+    if (idx->scalar == DAWN_SCALAR_F16 && idx->shadow_i8 && ws->eps_scale == 1.0f && n >= 65536 && !scan_only && idx->force_path != 1) {
+        shadow = idx->shadow.load();
+        kappa = idx->shadow_kappa.load();
+        if (!(shadow && idx->shadow_rows.load() >= n && kappa > 0.f)) shadow = nullptr;
+    }
     const bool use_gemm = gemm_ok && !scan_only && idx->force_path != 1 &&
                           (idx->force_path == 2 ||
                            ((int64_t)batch >= idx->gemm_min_batch && (int64_t)n >= idx->gemm_min_rows) ||
-                           ((int64_t)batch >= idx->gemm_small_batch && (int64_t)n >= idx->gemm_small_batch_rows));
-    if (use_gemm && idx->scalar == DAWN_SCALAR_F16 && idx->shadow_i8 && ws->eps_scale == 1.0f && n >= 65536) {
-        // the int8 shadow covers this snapshot (it is brought up to date before every search; rows are append-only)
-        const uint8_t *shadow = idx->shadow.load();
-        const float kappa = idx->shadow_kappa.load();
-        if (shadow && idx->shadow_rows.load() >= n && kappa > 0.f)
-            return search_f16_shadow(idx, ws, shadow, kappa, d_queries, batch, k, kprime, d_labels_out, d_dist_out, d_counts,
-                                     d_flags, s, d_status_out);
-    }
+                           ((int64_t)batch >= idx->gemm_small_batch && (int64_t)n >= idx->gemm_small_batch_rows) ||
+                           // with a shadow even a single query over a big corpus is cheaper through the int8 rounds (388 B per
+                           // row instead of the scan's 768 B; the rounds' fixed cost is ~0.25 ms): 10M rows 1.08 -> 0.85 ms,
+                           // 100M rows 11.9 -> 6.1 ms (tools/shadow_batch1.py)
+                           (shadow && (int64_t)n >= idx->shadow_single_rows));
+    if (use_gemm && shadow)
+        return search_f16_shadow(idx, ws, shadow, kappa, d_queries, batch, k, kprime, d_labels_out, d_dist_out, d_counts, d_flags, s,
+                                 d_status_out);
     if (use_gemm) {
         const size_t qp = (batch + 255) / 256 * 256;
         if ((rc = ensure_gemm_ws(idx, ws, gemm_workspace_bytes((int)batch)))) return rc;
@@ -1918,6 +1926,7 @@ int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value) {
     else if (!strcmp(key, "i8_tensor_chunk_rows")) idx->i8_tensor_chunk_rows = value < 65536 ? 65536 : value;
     else if (!strcmp(key, "i8_native")) idx->i8_native = value;
     else if (!strcmp(key, "shadow_i8")) idx->shadow_i8 = value;
+    else if (!strcmp(key, "shadow_single_rows")) idx->shadow_single_rows = value;
     else return fail(DAWN_ERR_INVALID, "unknown option '%s'", key);
     return DAWN_OK;
 }
