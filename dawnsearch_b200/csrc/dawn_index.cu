@@ -186,6 +186,7 @@ struct dawn_index {
     std::atomic<int64_t> i8_tensor_min_batch{16};
     std::atomic<int64_t> i8_tensor_chunk_rows{4 << 20};
     std::atomic<int64_t> shadow_i8{0};  // 1 = keep an int8 shadow of an fp16 corpus (+388 B per row) and filter on it
+    std::atomic<int64_t> shadow_big_k_rows{40000000};  // compute-bound batches with k > 32 take the shadow only from this many rows on
     std::atomic<int64_t> shadow_single_rows{6000000};  // with a shadow: from this many rows on, single queries take it too
     std::atomic<int64_t> i8_native{1};  // 1 = tcgen05 kind::i8 straight from the int8 arena, 0 = dequantise to fp16 tiles
 
@@ -1017,6 +1018,10 @@ int search_enqueue(dawn_index *idx, SearchWs *ws, const float *d_queries, size_t
                            // row instead of the scan's 768 B; the rounds' fixed cost is ~0.25 ms): 10M rows 1.08 -> 0.85 ms,
                            // 100M rows 11.9 -> 6.1 ms (tools/shadow_batch1.py)
                            (shadow && (int64_t)n >= idx->shadow_single_rows));
+    // A large k on a compute-bound batch over a small shard is the one case where the shadow loses: its wider filter band
+    // times k' = k + 4 candidates makes the exact re-scores between rounds cost more than the int8 tiles save (12.5M rows,
+    // 1024 queries, k = 100: 9.4 ms against 7.5 ms on the fp16 tiles; k = 20: 6.5 against 7.2; k = 10: 5.7 against 7.0).
+    if (shadow && batch >= 128 && k > 32 && (int64_t)n < idx->shadow_big_k_rows) shadow = nullptr;
     if (use_gemm && shadow)
         return search_f16_shadow(idx, ws, shadow, kappa, d_queries, batch, k, kprime, d_labels_out, d_dist_out, d_counts, d_flags, s,
                                  d_status_out);
@@ -1927,6 +1932,7 @@ int dawn_index_set_option(dawn_index *idx, const char *key, int64_t value) {
     else if (!strcmp(key, "i8_native")) idx->i8_native = value;
     else if (!strcmp(key, "shadow_i8")) idx->shadow_i8 = value;
     else if (!strcmp(key, "shadow_single_rows")) idx->shadow_single_rows = value;
+    else if (!strcmp(key, "shadow_big_k_rows")) idx->shadow_big_k_rows = value;
     else return fail(DAWN_ERR_INVALID, "unknown option '%s'", key);
     return DAWN_OK;
 }

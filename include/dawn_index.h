@@ -286,7 +286,8 @@ int dawn_index_set_profiling(dawn_index *idx, int enable);
  * batches that would take the fp16 tensor-core path are FILTERED on the copy by the int8 tensor cores instead -- half the
  * HBM bytes, twice the MMA rate -- while every candidate is re-scored on the fp16 rows: results stay bit-identical.
  * "shadow_single_rows" (6M): with a shadow, from this many rows on even a single query takes that path (388 B per row
- * instead of the scan's 768 B).
+ * instead of the scan's 768 B).  "shadow_big_k_rows" (40M): batches of >= 128 queries with k > 32 take it only from this many
+ * rows on (below, the exact re-scores of k + 4 candidates per round cost more than the int8 tiles save).
  * int8 corpora: "i8_tensor_min_batch" (16, 0 = never) -- from this batch size on the corpus is dequantised chunk by chunk
  * ("i8_tensor_chunk_rows", 4M) into an fp16 scratch and searched on the tensor cores; results stay bit-identical.
  * "gemm_cta_group", "gemm_chunk_tiles", "gemm_growth", "gemm_sequential_tiles": A/B knobs of the tensor-core path, 0 = automatic;

@@ -29,6 +29,7 @@ def shadow300k(dawn, oracle):
     idx = dawn.new_index(dawn.IndexOptions(capacity=n))
     idx.add_synthetic(SEED, 0, n)
     idx.set_option("shadow_i8", 1)
+    idx.set_option("shadow_big_k_rows", 0)  # take the shadow path whatever k (by default k > 32 waits for 40M rows)
     yield idx, n, oracle.synth_rows_f16(SEED, 0, n)
     idx.close()
 
@@ -61,6 +62,22 @@ def test_shadow_with_distance_limit(dawn, oracle, shadow300k):
             keep = int((wd[i] < limit).sum())
             assert gc[i] == keep
             assert (gl[i, :keep] == wl[i, :keep]).all() and (bits(gd[i, :keep]) == bits(wd[i, :keep])).all()
+
+
+def test_large_k_on_a_small_shard_stays_on_the_fp16_tiles(dawn, oracle, shadow300k):
+    idx, n, stored = shadow300k
+    qs = oracle.make_queries(SEED, 43, 200, n)
+    idx.set_option("shadow_big_k_rows", 40_000_000)
+    idx.profile(reset=True)
+    got100 = idx.search_batch(qs, 100)       # compute-bound batch, k > 32, small shard: fp16 tiles
+    got100_small = idx.search_batch(qs[:64], 100)  # one query tile: HBM-bound, the shadow's 388 B per row win
+    got20 = idx.search_batch(qs, 20)
+    p = idx.profile(reset=True)
+    idx.set_option("shadow_big_k_rows", 0)
+    assert p["gemm_batches"] == 3 and p["shadow_batches"] == 2
+    check(oracle, stored, None, qs, 100, got100)
+    check(oracle, stored, None, qs[:64], 100, got100_small)
+    check(oracle, stored, None, qs, 20, got20)
 
 
 def test_shadow_follows_appends_growth_and_load(dawn, oracle, tmp_path):
@@ -116,6 +133,7 @@ def test_shadow_adversarial_rows(dawn, oracle):
                          oracle.make_queries(SEED + 6, 3, 58, n)]).astype(np.float32)
     with dawn.new_index(dawn.IndexOptions(capacity=n)) as idx:
         idx.set_option("shadow_i8", 1)
+        idx.set_option("shadow_big_k_rows", 0)
         idx.add_batch(labels, rows)
         for k in (10, 100):
             idx.profile(reset=True)

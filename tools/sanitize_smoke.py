@@ -47,6 +47,18 @@ if which in ("all", "i8gemm"):
             gl, gd, cnt = idx.search_batch(q2[:b], 10)
             assert (gl[0] == O.search_i8(q8, sc, None, q2[0], 10)[0]).all()
         print("i8gemm ok", idx.profile()["gemm_batches"], flush=True)
+if which in ("all", "shadow"):
+    # fp16 corpus filtered through its int8 shadow (gemm_i8.cu in shadow mode + shadow_quantize_kernel); needs >= 65,536 rows
+    n8 = 66_000
+    with D.new_index(D.IndexOptions(capacity=n8)) as idx:
+        idx.set_option("shadow_i8", 1)
+        idx.add_synthetic(5, 0, n8)
+        st16 = O.synth_rows_f16(5, 0, n8)
+        q2 = O.make_queries(5, 7, 140, n8)
+        for b in (8, 140):
+            gl, gd, cnt = idx.search_batch(q2[:b], 10)
+            assert (gl[0] == O.search_f16(st16, None, q2[0], 10)[0]).all()
+        print("shadow ok", idx.profile()["shadow_batches"], flush=True)
 if which in ("all", "f32"):
     with D.new_index(D.IndexOptions(capacity=n, quantization=D.ScalarKind.F32)) as idx:
         idx.add_batch(labels, rows)
