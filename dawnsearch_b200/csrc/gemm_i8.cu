@@ -496,10 +496,18 @@ __global__ void __launch_bounds__(kSelThreads) select_i8_kernel(uint2 *__restric
     clear_arrive_slots(arrive, blockIdx.x, gridDim.x, threadIdx.x, kSelThreads);
     __shared__ unsigned long long s_prefix;
     __shared__ uint32_t hist[256];
-    __shared__ uint32_t s_need, s_out;
+    __shared__ uint32_t s_need, s_out, s_marked;
+    __shared__ float s_qn2;
     __shared__ __align__(16) float sq[kDim];
+    __shared__ uint16_t s_list[kSelCap];  // new entries that need the exact re-score
+    // rows of the entries being re-scored exactly, staged by the whole CTA: strides of 49 / 25 x 16 B keep the eight threads of a
+    // quarter warp on different 16-byte bank groups
+    constexpr int kPassRows = 24, kStride16 = 2 * kDim + 16, kStride8 = kDim + 16;
+    __shared__ __align__(16) uint8_t s_rows[kPassRows * kStride16];
+    __shared__ float s_scale[kPassRows];
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     uint2 *log_q = log_g + (size_t)q * log_cap;
     const uint32_t cnt = cnt_g[q];
     const int n = (int)min(cnt, (uint32_t)log_cap);
@@ -509,41 +517,130 @@ __global__ void __launch_bounds__(kSelThreads) select_i8_kernel(uint2 *__restric
         s_prefix = 0ull;
         s_need = (uint32_t)kp;
         s_out = 0u;
+        s_marked = 0u;
     }
     __syncthreads();
-    for (int i = tid; i < n; i += kSelThreads) {
+    // ---- stage A: a fast f32 score of every NEW entry, one warp per entry (coalesced row read, 12 elements per lane, fma +
+    // shuffle tree).  It differs from the exact (sequential, unfused) score by at most eta: both are within
+    // 384 * 2^-24 * |q| |x| of the real dot product.
+    float ql[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) ql[j] = sq[12 * lane + j];
+    if (warp == 0) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 12; j++) a = fmaf(ql[j], ql[j], a);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (lane == 0) s_qn2 = a;
+    }
+    for (int i = tid; i < kept; i += kSelThreads) {  // exact scores from the previous select
         const uint2 e = log_q[i];
-        float sc = __uint_as_float(e.x);
-        if (i >= kept && corpus16) {  // shadow mode: the truth is the fp16 row -- the oracle's sequential f32 sum over it
-            const uint4 *rp = reinterpret_cast<const uint4 *>(corpus16 + (size_t)e.y * kDim);
-            float acc = 0.0f;
-#pragma unroll 4
-            for (int c = 0; c < kDim / 8; c++) {
-                const uint4 u = __ldg(rp + c);
-                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float2 x = __half22float2(h[j]);
-                    acc = __fadd_rn(acc, __fmul_rn(sq[c * 8 + 2 * j], x.x));
-                    acc = __fadd_rn(acc, __fmul_rn(sq[c * 8 + 2 * j + 1], x.y));
-                }
-            }
-            sc = acc;
-        } else if (i >= kept) {  // exact re-score of a new entry
-            const uint4 *rp = reinterpret_cast<const uint4 *>(arena + i8_row_offset(e.y));
-            float acc = 0.0f;
+        keys[i] = ((unsigned long long)float_to_ordered(__uint_as_float(e.x)) << 32) | (unsigned long long)(~e.y);
+    }
 #pragma unroll 2
-            for (int c = 0; c < kDim / 16; c++) {
-                const uint4 u = __ldg(rp + c);
-                const int8_t *b8 = reinterpret_cast<const int8_t *>(&u);
+    for (int i = kept + warp; i < n; i += kSelThreads / 32) {
+        const uint32_t row = log_q[i].y;
+        float a = 0.f;
+        if (corpus16) {
+            const uint2 *src = reinterpret_cast<const uint2 *>(corpus16 + (size_t)row * kDim) + lane * 3;
+            uint2 u[3];
 #pragma unroll
-                for (int j = 0; j < 16; j++) acc = __fadd_rn(acc, __fmul_rn(sq[c * 16 + j], (float)b8[j]));
+            for (int j = 0; j < 3; j++) u[j] = __ldg(src + j);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const __half2 *h = reinterpret_cast<const __half2 *>(&u[j]);
+                const float2 x0 = __half22float2(h[0]), x1 = __half22float2(h[1]);
+                a = fmaf(ql[4 * j], x0.x, a);
+                a = fmaf(ql[4 * j + 1], x0.y, a);
+                a = fmaf(ql[4 * j + 2], x1.x, a);
+                a = fmaf(ql[4 * j + 3], x1.y, a);
             }
-            sc = __fmul_rn(*reinterpret_cast<const float *>(arena + i8_scale_offset(e.y)), acc);
+        } else {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(arena + i8_row_offset(row)) + lane * 3;
+            uint32_t u[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) u[j] = __ldg(src + j);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int8_t *b8 = reinterpret_cast<const int8_t *>(&u[j]);
+#pragma unroll
+                for (int e = 0; e < 4; e++) a = fmaf(ql[4 * j + e], (float)b8[e], a);
+            }
         }
-        keys[i] = ((unsigned long long)float_to_ordered(sc) << 32) | (unsigned long long)(~e.y);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (!corpus16) a *= *reinterpret_cast<const float *>(arena + i8_scale_offset(row));
+        if (lane == 0) keys[i] = ((unsigned long long)float_to_ordered(a) << 32) | (unsigned long long)(~row);
     }
     __syncthreads();
+    // ---- stage B: tau = the k'-th best fast score.  At least k' entries then have an exact score >= tau - eta, so an entry
+    // whose fast score is below tau - 2 eta (exact < tau - eta) is not among the k' best: only the others are re-scored exactly.
+    float cut = __int_as_float(0xff800000);
+    if (n >= kp && n > kept) {
+        const unsigned long long Kt = radix_select_kth(keys, n, kp, hist, &s_prefix, &s_need, tid);
+        const float eta = 6.0e-5f * fmaxf(1.0f, sqrtf(s_qn2)) * eps_scale;
+        cut = ordered_to_float((uint32_t)(Kt >> 32)) - 2.0f * eta;
+        __syncthreads();
+        if (tid == 0) {
+            s_prefix = 0ull;
+            s_need = (uint32_t)kp;
+        }
+    }
+    for (int i = kept + tid; i < n; i += kSelThreads) {
+        if (ordered_to_float((uint32_t)(keys[i] >> 32)) >= cut) s_list[atomicAdd(&s_marked, 1u)] = (uint16_t)i;
+        else keys[i] = (unsigned long long)i;  // dropped: below every real key (and distinct)
+    }
+    __syncthreads();
+    // ---- stage C: the exact score (the oracle's sequential f32 sum) of the marked entries, rows staged through shared memory
+    const int n_marked = (int)s_marked;
+    const int units = corpus16 ? 2 * kDim / 16 : kDim / 16;  // 16-byte pieces per row
+    const int stride = corpus16 ? kStride16 : kStride8;
+    for (int base = 0; base < n_marked; base += kPassRows) {
+        const int m = min(kPassRows, n_marked - base);
+        for (int u = tid; u < m * units; u += kSelThreads) {
+            const int r = u / units, j = u - r * units;
+            const uint32_t row = ~(uint32_t)keys[s_list[base + r]];
+            const uint8_t *src = corpus16 ? reinterpret_cast<const uint8_t *>(corpus16 + (size_t)row * kDim) : arena + i8_row_offset(row);
+            *reinterpret_cast<uint4 *>(s_rows + r * stride + j * 16) = __ldg(reinterpret_cast<const uint4 *>(src) + j);
+        }
+        if (!corpus16 && tid < m)
+            s_scale[tid] = *reinterpret_cast<const float *>(arena + i8_scale_offset(~(uint32_t)keys[s_list[base + tid]]));
+        __syncthreads();
+        if (tid < m) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(s_rows + tid * stride);
+            float acc = 0.0f;
+            if (corpus16) {
+#pragma unroll 4
+                for (int c = 0; c < kDim / 8; c++) {
+                    const uint4 u = rp[c];
+                    const float4 qa = *reinterpret_cast<const float4 *>(&sq[c * 8]), qb = *reinterpret_cast<const float4 *>(&sq[c * 8 + 4]);
+                    const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+                    const float2 x0 = __half22float2(h[0]), x1 = __half22float2(h[1]), x2 = __half22float2(h[2]), x3 = __half22float2(h[3]);
+                    acc = __fadd_rn(acc, __fmul_rn(qa.x, x0.x));
+                    acc = __fadd_rn(acc, __fmul_rn(qa.y, x0.y));
+                    acc = __fadd_rn(acc, __fmul_rn(qa.z, x1.x));
+                    acc = __fadd_rn(acc, __fmul_rn(qa.w, x1.y));
+                    acc = __fadd_rn(acc, __fmul_rn(qb.x, x2.x));
+                    acc = __fadd_rn(acc, __fmul_rn(qb.y, x2.y));
+                    acc = __fadd_rn(acc, __fmul_rn(qb.z, x3.x));
+                    acc = __fadd_rn(acc, __fmul_rn(qb.w, x3.y));
+                }
+            } else {
+#pragma unroll 2
+                for (int c = 0; c < kDim / 16; c++) {
+                    const uint4 u = rp[c];
+                    const int8_t *b8 = reinterpret_cast<const int8_t *>(&u);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) acc = __fadd_rn(acc, __fmul_rn(sq[c * 16 + j], (float)b8[j]));
+                }
+                acc = __fmul_rn(s_scale[tid], acc);
+            }
+            const int i = s_list[base + tid];
+            keys[i] = ((unsigned long long)float_to_ordered(acc) << 32) | (keys[i] & 0xffffffffull);
+        }
+        __syncthreads();
+    }
     const unsigned long long K = n >= kp ? radix_select_kth(keys, n, kp, hist, &s_prefix, &s_need, tid) : 0ull;
     for (int i = tid; i < n; i += kSelThreads) {
         const unsigned long long key = keys[i];
