@@ -35,6 +35,8 @@ extern "C" {
     fn dawn_batcher_search(b: *mut c_void, q: *const f32, k: usize, labels: *mut u64, dist: *mut f32, count: *mut usize) -> c_int;
     fn dawn_batcher_free(b: *mut c_void);
     fn dawn_index_verify(idx: *mut c_void, bad_rows: *mut usize, min_norm: *mut f32, max_norm: *mut f32) -> c_int;
+    fn dawn_index_set_option(idx: *mut c_void, key: *const c_char, value: i64) -> c_int;
+    fn dawn_multi_set_option(m: *mut c_void, key: *const c_char, value: i64) -> c_int;
     // several GPUs, one process: shards + one NCCL all-gather + device merge inside the library
     fn dawn_multi_create(devices: *const c_int, n_devices: usize, scalar: u32, out: *mut *mut c_void) -> c_int;
     fn dawn_multi_free(m: *mut c_void);
@@ -155,6 +157,14 @@ impl Index {
         ck(unsafe { dawn_index_verify(self.h, &mut bad, &mut lo, &mut hi) })?;
         Ok((bad, lo, hi))
     }
+    /// Tuning knobs of the library (include/dawn_index.h).  The one a deployment may want: `set_option("shadow_i8", 1)` --
+    /// the fp16 corpus also keeps an int8 copy of itself (+388 B per page) that is only used to FILTER on the int8 tensor
+    /// cores; every candidate is re-scored on the fp16 rows, so results do not change, batches run ~1.7x faster and a single
+    /// query over a big corpus takes half the time.
+    pub fn set_option(&self, key: &str, value: i64) -> anyhow::Result<()> {
+        let k = std::ffi::CString::new(key)?;
+        ck(unsafe { dawn_index_set_option(self.h, k.as_ptr(), value) })
+    }
 }
 
 impl Drop for Index { fn drop(&mut self) { unsafe { dawn_index_free(self.h) } } }
@@ -205,6 +215,11 @@ impl MultiIndex {
         mck(unsafe { dawn_multi_search_batch(self.m, queries.as_ptr(), b, count, labels.as_mut_ptr(), distances.as_mut_ptr(), counts.as_mut_ptr()) })?;
         Ok((0..b).map(|i| Matches { labels: labels[i * count..i * count + counts[i]].to_vec(),
                                     distances: distances[i * count..i * count + counts[i]].to_vec() }).collect())
+    }
+    /// Forwarded to every shard (e.g. `"shadow_i8"`); `"exchange"`: 0 auto, 1 peer copies, 2 NCCL.
+    pub fn set_option(&self, key: &str, value: i64) -> anyhow::Result<()> {
+        let k = std::ffi::CString::new(key)?;
+        mck(unsafe { dawn_multi_set_option(self.m, k.as_ptr(), value) })
     }
     pub fn size(&self) -> usize { unsafe { dawn_multi_size(self.m) } }
     pub fn capacity(&self) -> usize { unsafe { dawn_multi_capacity(self.m) } }
