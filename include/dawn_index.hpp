@@ -232,11 +232,22 @@ public:
         check(dawn_index_get_i24(h_, label, v.data()));
         return v;
     }
+    // SearchProvider::verify over the device corpus (search_provider.rs:289-327): rows failing the norm gate, min / max norm.
+    struct VerifyResult { std::size_t bad_rows; float min_norm, max_norm; };
+    VerifyResult verify() const {
+        VerifyResult r{0, 0.f, 0.f};
+        check(dawn_index_verify(h_, &r.bad_rows, &r.min_norm, &r.max_norm));
+        return r;
+    }
+    // Tuning knobs (dawn_index.h).  set_option("shadow_i8", 1): the fp16 corpus also keeps an int8 copy of itself that is only
+    // used to FILTER on the int8 tensor cores; candidates are re-scored on the fp16 rows, results do not change.
+    void set_option(const std::string &key, std::int64_t value) const { check(dawn_index_set_option(h_, key.c_str(), value)); }
     dawn_index *handle() const { return h_; }
 };
 
 // Micro-batching front for SearchService (src/search/search_service.rs:55-104): many threads call search() with one
-// query each, a worker thread inside the library answers them in batches.  Must not outlive the index.
+// query each and are answered in batches (what arrived while the previous batch was on the GPU; a lone caller never waits).
+// Must not outlive the index.
 class Batcher {
     dawn_batcher *b_ = nullptr;
 
